@@ -1,0 +1,305 @@
+// capi.cu — the extern "C" boundary (include/bridgelang_b200.h) and the host-side schedule of the towers,
+// the projector and the fused featurize+project path.  All device work is the hand-written kernels in
+// this directory; there is no library GEMM, no CPU fallback and no synchronisation in here.
+#include "../../include/bridgelang_b200.h"
+
+#include <algorithm>
+
+#include "gemm.h"
+
+using namespace blb;
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bfloat16*>(p); }
+inline __nv_bfloat16* bf(void* p) { return static_cast<__nv_bfloat16*>(p); }
+
+constexpr int PATCHES = 256;  // 224 / 14 squared
+
+struct TowerWs {
+  size_t resid, xn, big, total;
+};
+
+// resid fp32 [M,D] | xn bf16 [M,D] (LayerNorm out, then attention out) | big bf16 [M, max(3D, Hm_pad)]
+// (im2col staging, then packed qkv, then the MLP hidden — lifetimes never overlap)
+TowerWs tower_ws(const blb_vit_weights* w, int batch) {
+  const size_t T = PATCHES + w->n_prefix, M = static_cast<size_t>(batch) * T, D = w->dim;
+  const size_t wide = std::max<size_t>(std::max<size_t>(3 * D, w->hidden_pad), w->patch_ldk);
+  TowerWs s;
+  s.resid = 0;
+  s.xn = align_up(M * D * 4);
+  s.big = s.xn + align_up(M * D * 2);
+  s.total = s.big + align_up(M * wide * 2);
+  return s;
+}
+
+int check_vit(const blb_vit_weights* w) {
+  if (w == nullptr || w->blocks_host == nullptr || w->patch_w == nullptr || w->patch_b == nullptr ||
+      w->pos_embed == nullptr)
+    return BLB_ERR_ARG;
+  if (w->dim != w->heads * w->head_dim || w->n_blocks <= 0 || w->n_prefix < 0) return BLB_ERR_ARG;
+  if (w->n_prefix > 0 && w->prefix == nullptr) return BLB_ERR_ARG;
+  if (w->dim % 128 != 0 || w->hidden_pad % 128 != 0 || w->patch_ldk % 8 != 0 || w->patch_ldk < 588)
+    return BLB_ERR_SHAPE;
+  return 0;
+}
+
+#define BLB_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void* out, int ld_out, int out_col_off,
+                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  BLB_TRY(check_vit(w));
+  if (pixels == nullptr || out == nullptr || workspace == nullptr || batch <= 0) return BLB_ERR_ARG;
+  const TowerWs ws = tower_ws(w, batch);
+  if (workspace_bytes < ws.total) return BLB_ERR_WORKSPACE;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  float* resid = reinterpret_cast<float*>(base + ws.resid);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.xn);
+  __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(base + ws.big);
+  const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
+
+  // --- PatchEmbed (+bias +pos_embed) and the cls/reg prefix rows: timm patch_embed + _pos_embed ---------
+  BLB_TRY(im2col_patch14(bf(pixels), big, batch, w->patch_ldk, st));
+  {
+    GemmEpilogue e;
+    e.bias = w->patch_b;
+    e.pos = w->pos_embed;
+    e.resid = resid;
+    e.ld_resid = D;
+    e.tok_in = PATCHES;
+    e.tok_out = T;
+    e.tok_shift = w->n_prefix;
+    BLB_TRY(gemm_bf16(big, w->patch_ldk, bf(w->patch_w), w->patch_ldk, batch * PATCHES, D, w->patch_ldk, EPI_PATCH, e,
+                      st));
+  }
+  BLB_TRY(write_prefix_tokens(w->prefix, resid, batch, T, w->n_prefix, D, st));
+
+  // --- timm Block x n_blocks:  x += ls1(attn(norm1(x)));  x += ls2(mlp(norm2(x))) -----------------------
+  for (int i = 0; i < w->n_blocks; ++i) {
+    const blb_block_weights& b = w->blocks_host[i];
+    const bool last = i == w->n_blocks - 1;
+    BLB_TRY(layernorm_f32_bf16(resid, D, b.ln1_w, b.ln1_b, xn, D, M, D, w->ln_eps, st));
+    {
+      GemmEpilogue e;
+      e.bias = b.qkv_b;
+      e.out = big;
+      e.ld_out = 3 * D;
+      BLB_TRY(gemm_bf16(xn, D, bf(b.qkv_w), D, M, 3 * D, D, EPI_BIAS, e, st));
+    }
+    BLB_TRY(attention_bf16(big, xn, batch, T, w->heads, w->head_dim, st));
+    {
+      GemmEpilogue e;
+      e.bias = b.proj_b;
+      e.gamma = b.ls1;
+      e.resid = resid;
+      e.ld_resid = D;
+      BLB_TRY(gemm_bf16(xn, D, bf(b.proj_w), D, M, D, D, EPI_RESIDUAL, e, st));
+    }
+    BLB_TRY(layernorm_f32_bf16(resid, D, b.ln2_w, b.ln2_b, xn, D, M, D, w->ln_eps, st));
+    {
+      GemmEpilogue e;
+      e.bias = b.fc1_b;
+      e.out = big;
+      e.ld_out = Hm;
+      BLB_TRY(gemm_bf16(xn, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
+    }
+    {
+      GemmEpilogue e;
+      e.bias = b.fc2_b;
+      e.gamma = b.ls2;
+      e.resid = resid;
+      e.ld_resid = D;
+      if (last) {
+        // get_intermediate_layers(n={depth-2}) + prefix drop + torch.cat(dim=2): the last needed block's
+        // epilogue stores the patch rows straight into this tower's column slice of [B*256, 2176].
+        e.out = bf(out);
+        e.ld_out = ld_out;
+        e.out_col_off = out_col_off;
+        e.tok_in = T;
+        e.tok_out = PATCHES;
+        e.tok_shift = -w->n_prefix;
+      }
+      BLB_TRY(gemm_bf16(big, Hm, bf(b.fc2_w), Hm, M, D, Hm, EPI_RESIDUAL, e, st));
+    }
+  }
+  return 0;
+}
+
+size_t projector_ws(const blb_projector_weights* w, int rows) {
+  return align_up(static_cast<size_t>(rows) * w->hidden_dim * 2) + align_up(static_cast<size_t>(rows) * w->out_dim * 2);
+}
+
+int projector_forward(const blb_projector_weights* w, const void* x, int ldx, int rows, void* out, int ld_out,
+                      int tok_in, int tok_out, int tok_shift, void* workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
+  if (w == nullptr || x == nullptr || out == nullptr || workspace == nullptr || rows <= 0) return BLB_ERR_ARG;
+  if (w->fc1_w == nullptr || w->fc2_w == nullptr || w->fc3_w == nullptr) return BLB_ERR_ARG;
+  if (workspace_bytes < projector_ws(w, rows)) return BLB_ERR_WORKSPACE;
+  __nv_bfloat16* h1 = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(workspace) +
+                                                       align_up(static_cast<size_t>(rows) * w->hidden_dim * 2));
+  GemmEpilogue e1;
+  e1.bias = w->fc1_b;
+  e1.out = h1;
+  e1.ld_out = w->hidden_dim;
+  BLB_TRY(gemm_bf16(bf(x), ldx, bf(w->fc1_w), w->in_dim, rows, w->hidden_dim, w->in_dim, EPI_BIAS_GELU, e1, st));
+  GemmEpilogue e2;
+  e2.bias = w->fc2_b;
+  e2.out = h2;
+  e2.ld_out = w->out_dim;
+  BLB_TRY(gemm_bf16(h1, w->hidden_dim, bf(w->fc2_w), w->hidden_dim, rows, w->out_dim, w->hidden_dim, EPI_BIAS_GELU, e2,
+                    st));
+  GemmEpilogue e3;
+  e3.bias = w->fc3_b;
+  e3.out = bf(out);
+  e3.ld_out = ld_out;
+  e3.tok_in = tok_in;
+  e3.tok_out = tok_out;
+  e3.tok_shift = tok_shift;
+  BLB_TRY(gemm_bf16(h2, w->out_dim, bf(w->fc3_w), w->out_dim, rows, w->out_dim, w->out_dim, EPI_BIAS, e3, st));
+  return 0;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int blb_abi_version(void) { return 1; }
+
+const char* blb_status_string(int status) {
+  switch (status) {
+    case BLB_OK: return "ok";
+    case BLB_ERR_ARG: return "bad argument (null pointer or non-positive size)";
+    case BLB_ERR_SHAPE: return "shape not supported by the sm_100a tiling";
+    case BLB_ERR_ALIGN: return "pointer or row pitch not 16-byte aligned";
+    case BLB_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    case BLB_ERR_WORKSPACE: return "workspace too small";
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown status";
+}
+
+long long blb_launch_count(void) { return launch_count(); }
+void blb_set_gemm_cta_group(int ctas) { gemm_set_cta_group(ctas); }
+
+int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int mode,
+                  const blb_epilogue* epi, void* stream) {
+  if (epi == nullptr) return BLB_ERR_ARG;
+  GemmEpilogue e;
+  e.bias = epi->bias;
+  e.gamma = epi->gamma;
+  e.resid = epi->resid;
+  e.ld_resid = epi->ld_resid;
+  e.out = bf(epi->out);
+  e.ld_out = epi->ld_out;
+  e.out_col_off = epi->out_col_off;
+  e.pos = epi->pos;
+  e.tok_in = epi->tok_in;
+  e.tok_out = epi->tok_out;
+  e.tok_shift = epi->tok_shift;
+  if (mode == EPI_BIAS || mode == EPI_BIAS_GELU) {
+    if (e.out == nullptr || e.ld_out % 8 != 0 || e.out_col_off % 8 != 0) return BLB_ERR_ARG;
+  } else if (mode == EPI_RESIDUAL) {
+    if (e.resid == nullptr || e.ld_resid % 4 != 0) return BLB_ERR_ARG;
+    if (e.out != nullptr && (e.ld_out % 8 != 0 || e.out_col_off % 8 != 0)) return BLB_ERR_ARG;
+  } else if (mode == EPI_PATCH) {
+    if (e.resid == nullptr || e.pos == nullptr || e.tok_in <= 0 || e.ld_resid % 4 != 0) return BLB_ERR_ARG;
+  } else {
+    return BLB_ERR_ARG;
+  }
+  return gemm_bf16(bf(A), lda, bf(W), ldw, M, N, K, mode, e, as_stream(stream));
+}
+
+int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void* y, int ldy, int rows, int D,
+                  float eps, void* stream) {
+  return layernorm_f32_bf16(x, ldx, w, b, bf(y), ldy, rows, D, eps, as_stream(stream));
+}
+
+int blb_attention(const void* qkv, void* out, int B, int T, int H, int head_dim, void* stream) {
+  return attention_bf16(bf(qkv), bf(out), B, T, H, head_dim, as_stream(stream));
+}
+
+int blb_im2col_patch14(const void* pixels, void* cols, int B, int ldk, void* stream) {
+  return im2col_patch14(bf(pixels), bf(cols), B, ldk, as_stream(stream));
+}
+
+size_t blb_vit_workspace_bytes(const blb_vit_weights* w, int batch) {
+  if (w == nullptr || batch <= 0) return 0;
+  return tower_ws(w, batch).total;
+}
+
+int blb_vit_tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void* out, int ld_out,
+                          int out_col_off, void* workspace, size_t workspace_bytes, void* stream) {
+  if (ld_out % 8 != 0 || out_col_off % 8 != 0) return BLB_ERR_ARG;
+  return tower_forward(w, pixels, batch, out, ld_out, out_col_off, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t blb_projector_workspace_bytes(const blb_projector_weights* w, int rows) {
+  if (w == nullptr || rows <= 0) return 0;
+  return projector_ws(w, rows);
+}
+
+int blb_projector_forward(const blb_projector_weights* w, const void* x, int ldx, int rows, void* out, int ld_out,
+                          int tok_in, int tok_out, int tok_shift, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (ld_out % 8 != 0) return BLB_ERR_ARG;
+  return projector_forward(w, x, ldx, rows, out, ld_out, tok_in, tok_out, tok_shift, workspace, workspace_bytes,
+                           as_stream(stream));
+}
+
+size_t blb_fused_workspace_bytes(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                 const blb_projector_weights* proj, int batch) {
+  if (dino == nullptr || siglip == nullptr || batch <= 0) return 0;
+  size_t s = std::max(tower_ws(dino, batch).total, tower_ws(siglip, batch).total);
+  if (proj != nullptr) s = std::max(s, projector_ws(proj, batch * PATCHES));
+  return s;
+}
+
+int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                        const blb_projector_weights* proj, const void* pixels_dino,
+                                        const void* pixels_siglip, int batch, void* features, void* projected,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (dino == nullptr || siglip == nullptr || features == nullptr) return BLB_ERR_ARG;
+  if (proj != nullptr && projected == nullptr) return BLB_ERR_ARG;
+  if (workspace_bytes < blb_fused_workspace_bytes(dino, siglip, proj, batch)) return BLB_ERR_WORKSPACE;
+  const int fused_dim = dino->dim + siglip->dim;
+  if (proj != nullptr && proj->in_dim != fused_dim) return BLB_ERR_SHAPE;
+  cudaStream_t st = as_stream(stream);
+  // dinosiglip_vit.py:144-147: dino patches | siglip patches, concatenated on the channel dim
+  BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, workspace_bytes, st));
+  BLB_TRY(tower_forward(siglip, pixels_siglip, batch, features, fused_dim, dino->dim, workspace, workspace_bytes, st));
+  if (proj != nullptr)
+    BLB_TRY(projector_forward(proj, features, fused_dim, batch * PATCHES, projected, proj->out_dim, 0, 0, 0, workspace,
+                              workspace_bytes, st));
+  return 0;
+}
+
+int blb_argmax(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, void* stream) {
+  return argmax_rows(logits, dtype, rows, vocab, ld, ids, as_stream(stream));
+}
+
+int blb_detokenize_unnormalize(const int64_t* ids, int n, int vocab_size, const double* bin_centers, int n_centers,
+                               int action_dim, const double* q01, const double* q99, const uint8_t* mask,
+                               double* normalized_out, double* actions_out, void* stream) {
+  return detokenize_unnormalize(ids, n, vocab_size, bin_centers, n_centers, action_dim, q01, q99, mask, normalized_out,
+                                actions_out, as_stream(stream));
+}
+
+int blb_argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int vocab_size,
+                                      const double* bin_centers, int n_centers, int action_dim, const double* q01,
+                                      const double* q99, const uint8_t* mask, int64_t* ids, double* normalized_out,
+                                      double* actions_out, void* stream) {
+  if (bin_centers == nullptr) return BLB_ERR_ARG;
+  return argmax_detokenize_unnormalize(logits, dtype, rows, vocab, ld, vocab_size, bin_centers, n_centers, action_dim,
+                                       q01, q99, mask, ids, normalized_out, actions_out, as_stream(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,66 @@
+// gemm.h — internal C++ interface shared by the kernels in csrc/ (not part of the C ABI).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/bridgelang_b200.h"
+
+namespace blb {
+
+// status codes BLB_OK / BLB_ERR_* come from the public header
+
+enum GemmEpilogueMode : int {
+  EPI_BIAS = 0,       // out_bf16 = acc + bias
+  EPI_BIAS_GELU = 1,  // out_bf16 = gelu_erf(acc + bias)
+  EPI_RESIDUAL = 2,   // resid_f32 += gamma * (acc + bias); optional bf16 copy of the new residual (row-remapped)
+  EPI_PATCH = 3       // resid_f32[remap(row)] = acc + bias + pos[token]
+};
+
+struct GemmEpilogue {
+  const float* bias = nullptr;    // [N]
+  const float* gamma = nullptr;   // [N] LayerScale (nullptr → 1)
+  float* resid = nullptr;         // fp32 residual stream
+  int ld_resid = 0;
+  __nv_bfloat16* out = nullptr;   // bf16 destination
+  int ld_out = 0;
+  int out_col_off = 0;
+  const float* pos = nullptr;     // [tok_in, N] position embedding (EPI_PATCH)
+  // row remap image-wise: src row = b*tok_in + t  →  dst row = b*tok_out + t + tok_shift (dropped if out of range)
+  int tok_in = 0;                 // 0 → identity
+  int tok_out = 0;
+  int tok_shift = 0;
+};
+
+int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, int mode,
+              const GemmEpilogue& epi, cudaStream_t stream);
+void gemm_set_cta_group(int ctas);
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int num_sms();
+long long launch_count();
+void count_launch(int n);
+
+// layernorm.cu — timm LayerNorm(eps) over the last dim of an fp32 [rows, D] stream → bf16
+int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y, int ldy, int rows,
+                       int D, float eps, cudaStream_t stream);
+
+// attention.cu — softmax(q kᵀ · hd^-0.5) v over packed qkv [B*T, 3*H*hd] → out [B*T, H*hd]
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream);
+
+// patch_embed.cu — im2col for Conv2d(3, D, 14, stride 14) and the cls/reg prefix rows
+int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int ldk, cudaStream_t stream);
+int write_prefix_tokens(const float* prefix, float* resid, int B, int T, int n_prefix, int D, cudaStream_t stream);
+
+// decode_tail.cu
+int argmax_rows(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, cudaStream_t stream);
+int detokenize_unnormalize(const int64_t* ids, int n, int vocab_size, const double* bin_centers, int n_centers,
+                           int action_dim, const double* q01, const double* q99, const uint8_t* mask, double* norm_out,
+                           double* act_out, cudaStream_t stream);
+int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int vocab_size,
+                                  const double* bin_centers, int n_centers, int action_dim, const double* q01,
+                                  const double* q99,
+                                  const uint8_t* mask, int64_t* ids, double* norm_out, double* act_out,
+                                  cudaStream_t stream);
+
+}  // namespace blb

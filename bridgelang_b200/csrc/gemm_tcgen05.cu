@@ -1,0 +1,416 @@
+// gemm_tcgen05.cu — persistent, warp-specialised bf16 GEMM for sm_100a with fused epilogues.
+//
+//   C[M,N] = A[M,K] · W[N,K]^T   (A activations row-major, W = nn.Linear weight, both K-major)
+//
+// This one kernel replaces every cuBLASLt call + trailing elementwise kernel that the reference
+// reaches through timm / nn.Sequential:
+//   timm Attention.qkv / proj, Mlp.fc1 / fc2, LayerScale, residual add, PatchEmbed (as GEMM)
+//   prismatic/util/nn_utils.py:42-48 (FusedMLPProjector Linear+GELU chain)
+//
+// Structure (one CTA, or a cta_group::2 CTA pair, per SM; static persistent tile schedule):
+//   warp 0      TMA producer   (cp.async.bulk.tensor → 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM)
+//   warp 2      TMEM allocator
+//   warp 3      idle
+//   warps 4-11  epilogue       (tcgen05.ld → registers → fused bias/GELU/LayerScale/residual → global)
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace blb {
+
+constexpr int BM = 128;          // rows per CTA (UMMA M = 128 per CTA; 256 for a CTA pair)
+constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+template <int BN, int CTAS>
+struct GemmCfg {
+  static constexpr int B_ROWS = BN / CTAS;                 // rows of W this CTA stages per k-block
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 512;                    // 2 accumulator stages of BN (<=256) columns
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ bool map_row(const GemmEpilogue& e, int row, int& dst_row, int& tok) {
+  if (e.tok_in <= 0) {
+    dst_row = row;
+    tok = 0;
+    return true;
+  }
+  int b = row / e.tok_in;
+  tok = row - b * e.tok_in;
+  int t2 = tok + e.tok_shift;
+  dst_row = b * e.tok_out + t2;
+  return t2 >= 0 && t2 < e.tok_out;
+}
+
+template <int BN, int CTAS, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
+                 int K, GemmEpilogue epi) {
+  using Cfg = GemmCfg<BN, CTAS>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]   TMA → MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA → TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]        MMA → epilogue
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]        epilogue → MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  const int tile_m = BM * CTAS;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
+  const int n_tiles = N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+  const int first_tile = blockIdx.x / CTAS;
+  const int tile_step = gridDim.x / CTAS;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], CTAS * NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CTAS>(tmem_slot, Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ==========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m_blk = tile / n_tiles;
+        const int n_blk = tile - m_blk * n_tiles;
+        const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
+        const int row_b = n_blk * BN + static_cast<int>(cta_rank) * Cfg::B_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if constexpr (CTAS == 1) {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BK, row_a);
+            tma_load_2d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BK, row_b);
+          } else {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kb * BK, row_a);
+            tma_load_2d_2sm(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage], kb * BK, row_b);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ===========================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CTAS, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * Cfg::ACC_STRIDE);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::A_BYTES));
+          const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // +32 bytes per UMMA_K step inside the 128-byte swizzle row → +2 in the (addr>>4) field
+            umma_bf16<CTAS>(tmem_d, desc_a + static_cast<uint64_t>(2 * k), desc_b + static_cast<uint64_t>(2 * k),
+                            idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<CTAS>(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) umma_commit<CTAS>(&tfull_bar[acc]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue ============================================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may touch (= warp_id % 4)
+    const int half = ew >> 2;                  // which half of the BN columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int CHUNKS = COLS_PER_WARP / 32;
+    static_assert(COLS_PER_WARP % 32 == 0, "BN/2 must be a multiple of 32");
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int row = m_blk * tile_m + static_cast<int>(cta_rank) * BM + quarter * 32 + lane;
+      const bool row_ok = row < M;
+      int dst_row = row, tok = 0;
+      bool dst_ok = row_ok;
+      dst_ok = map_row(epi, row, dst_row, tok) && row_ok;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col_in_tile = half * COLS_PER_WARP + c * 32;
+        const int col0 = n_blk * BN + col_in_tile;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                          static_cast<uint32_t>(acc * Cfg::ACC_STRIDE + col_in_tile),
+                      r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (epi.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if constexpr (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU) {
+          if constexpr (MODE == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (dst_ok) {
+            __nv_bfloat16* o = epi.out + static_cast<size_t>(dst_row) * epi.ld_out + epi.out_col_off + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              pk.x = pack_bf16x2(v[j], v[j + 1]);
+              pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        } else if constexpr (MODE == EPI_PATCH) {
+          // out_f32[dst_row, col] = acc + bias + pos_embed[token, col]   (timm PatchEmbed + _pos_embed)
+          if (dst_ok) {
+            const float* p = epi.pos + static_cast<size_t>(tok) * N + col0;
+            float* x = epi.resid + static_cast<size_t>(dst_row) * epi.ld_resid + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 p4 = __ldg(reinterpret_cast<const float4*>(p + j));
+              float4 o4 = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
+              *reinterpret_cast<float4*>(x + j) = o4;
+            }
+          }
+        } else {  // EPI_RESIDUAL:  x += gamma * (acc + bias)   (timm Block: x + ls(branch(x)))
+          if (row_ok) {
+            float* x = epi.resid + static_cast<size_t>(row) * epi.ld_resid + col0;
+            if (epi.gamma != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(epi.gamma + col0 + j));
+                v[j] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 x4 = *reinterpret_cast<const float4*>(x + j);
+              x4.x += v[j]; x4.y += v[j + 1]; x4.z += v[j + 2]; x4.w += v[j + 3];
+              v[j] = x4.x; v[j + 1] = x4.y; v[j + 2] = x4.z; v[j + 3] = x4.w;
+              *reinterpret_cast<float4*>(x + j) = x4;
+            }
+            if (epi.out != nullptr && dst_ok) {
+              __nv_bfloat16* o = epi.out + static_cast<size_t>(dst_row) * epi.ld_out + epi.out_col_off + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                pk.x = pack_bf16x2(v[j], v[j + 1]);
+                pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete → hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CTAS == 1) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(&tempty_bar[acc], 0);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (CTAS == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<CTAS>(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, cols] row-major (pitch ld elements) → TMA map with a {64, box_rows} box, 128B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return BLB_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return BLB_ERR_ALIGN;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : BLB_ERR_DRIVER;
+}
+
+static int g_num_sms = 0;
+static int g_force_ctas = 0;   // 0 = auto, 1 / 2 = forced (tests and A/B measurements)
+static long long g_launches = 0;
+
+void gemm_set_cta_group(int ctas) { g_force_ctas = ctas; }
+long long launch_count() { return g_launches; }
+void count_launch(int n) { g_launches += n; }
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int BN, int CTAS, int MODE>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& epi,
+                  cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CTAS>;
+  auto kern = gemm_bf16_kernel<BN, CTAS, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int tile_m = BM * CTAS;
+  const int tiles = ((M + tile_m - 1) / tile_m) * (N / BN);
+  int ctas = num_sms();
+  if (CTAS == 2) ctas &= ~1;
+  if (tiles * CTAS < ctas) ctas = tiles * CTAS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, epi);
+  count_launch(1);
+  return static_cast<int>(e);
+}
+
+template <int BN, int CTAS>
+static int launch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                       const GemmEpilogue& epi, cudaStream_t s) {
+  switch (mode) {
+    case EPI_BIAS: return launch<BN, CTAS, EPI_BIAS>(ta, tb, M, N, K, epi, s);
+    case EPI_BIAS_GELU: return launch<BN, CTAS, EPI_BIAS_GELU>(ta, tb, M, N, K, epi, s);
+    case EPI_RESIDUAL: return launch<BN, CTAS, EPI_RESIDUAL>(ta, tb, M, N, K, epi, s);
+    case EPI_PATCH: return launch<BN, CTAS, EPI_PATCH>(ta, tb, M, N, K, epi, s);
+  }
+  return BLB_ERR_ARG;
+}
+
+int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, int mode,
+              const GemmEpilogue& epi, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || A == nullptr || W == nullptr) return BLB_ERR_ARG;
+  int bn = 0;
+  if (N % 256 == 0) bn = 256;
+  else if (N % 192 == 0) bn = 192;
+  else if (N % 128 == 0) bn = 128;
+  else return BLB_ERR_SHAPE;
+  const int ctas = g_force_ctas != 0 ? g_force_ctas : 2;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);
+  if (rc != 0) return rc;
+  rc = make_tmap_bf16_2d(&tb, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldw),
+                         static_cast<uint32_t>(bn / ctas));
+  if (rc != 0) return rc;
+  if (ctas == 1) {
+    if (bn == 256) return launch_mode<256, 1>(mode, ta, tb, M, N, K, epi, stream);
+    if (bn == 192) return launch_mode<192, 1>(mode, ta, tb, M, N, K, epi, stream);
+    return launch_mode<128, 1>(mode, ta, tb, M, N, K, epi, stream);
+  }
+  if (bn == 256) return launch_mode<256, 2>(mode, ta, tb, M, N, K, epi, stream);
+  if (bn == 192) return launch_mode<192, 2>(mode, ta, tb, M, N, K, epi, stream);
+  return launch_mode<128, 2>(mode, ta, tb, M, N, K, epi, stream);
+}
+
+}  // namespace blb

@@ -1,0 +1,71 @@
+// layernorm.cu — fused LayerNorm over the fp32 residual stream, bf16 output (the GEMM A operand).
+//
+// Replaces timm Block.norm1 / norm2 = nn.LayerNorm(D, eps=1e-6): biased variance,
+// fp32 statistics, affine.  One warp per token row; the row lives in registers between the
+// mean pass, the variance pass (about the mean, like ATen) and the normalise/store pass, so HBM
+// sees exactly one fp32 read and one bf16 write per element (6 B/element — the roofline for this op).
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace blb {
+
+template <int VEC>  // D = VEC * 128
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        __nv_bfloat16* __restrict__ y, int ldy, int rows, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  constexpr int D = VEC * 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+  float4 v[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) v[j] = xr[lane + 32 * j];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float a = v[j].x - mean, c = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+    q += (a * a + c * c) + (d * d + e * e);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / D) + eps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float4 ww = __ldg(w4 + lane + 32 * j);
+    const float4 bb = __ldg(b4 + lane + 32 * j);
+    uint2 o;
+    o.x = pack_bf16x2((v[j].x - mean) * rstd * ww.x + bb.x, (v[j].y - mean) * rstd * ww.y + bb.y);
+    o.y = pack_bf16x2((v[j].z - mean) * rstd * ww.z + bb.z, (v[j].w - mean) * rstd * ww.w + bb.w);
+    yr[lane + 32 * j] = o;
+  }
+}
+
+int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y, int ldy, int rows,
+                       int D, float eps, cudaStream_t stream) {
+  if (x == nullptr || w == nullptr || b == nullptr || y == nullptr || rows <= 0) return BLB_ERR_ARG;
+  if (D % 128 != 0 || D > 2048 || ldx % 4 != 0 || ldy % 4 != 0) return BLB_ERR_SHAPE;
+  const dim3 grid((rows + 7) / 8), block(256);
+  switch (D / 128) {
+#define BLB_LN_CASE(V) \
+  case V: layernorm_kernel<V><<<grid, block, 0, stream>>>(x, ldx, w, b, y, ldy, rows, eps); break;
+    BLB_LN_CASE(1) BLB_LN_CASE(2) BLB_LN_CASE(3) BLB_LN_CASE(4) BLB_LN_CASE(5) BLB_LN_CASE(6) BLB_LN_CASE(7)
+    BLB_LN_CASE(8) BLB_LN_CASE(9) BLB_LN_CASE(10) BLB_LN_CASE(11) BLB_LN_CASE(12) BLB_LN_CASE(13)
+    BLB_LN_CASE(14) BLB_LN_CASE(15) BLB_LN_CASE(16)
+#undef BLB_LN_CASE
+    default: return BLB_ERR_SHAPE;
+  }
+  count_launch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace blb

@@ -1,0 +1,65 @@
+// patch_embed.cu — staging for timm PatchEmbed = Conv2d(3, D, kernel 14, stride 14, bias) run as a GEMM
+// (SURVEY.md §2 K1/K2, §8 a4/a5).
+//
+// im2col_patch14: pixels [B,3,224,224] bf16 → cols [B*256, ldk] bf16 with column index k = c*196 + kh*14 + kw,
+// i.e. exactly the flattening order of the conv weight [D,3,14,14] → [D,588]; patch rows are ordered h then w
+// (flatten(2).transpose(1,2)).  Columns 588..ldk-1 are zero so the row pitch is 16-byte aligned for TMA.
+// The conv bias and the position embedding are added by the GEMM epilogue (EPI_PATCH).
+//
+// write_prefix_tokens: DINOv2-reg4 prepends cls + 4 register tokens *after* the pos-embed add
+// (no_embed_class=True), so those 5 rows of the residual stream are input independent.
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace blb {
+
+constexpr int IMG = 224, PATCH = 14, GRID_P = 16, KREAL = 3 * PATCH * PATCH;  // 588
+
+__global__ void __launch_bounds__(256) im2col_kernel(const __nv_bfloat16* __restrict__ px,
+                                                     __nv_bfloat16* __restrict__ cols, int B, int ldk) {
+  // one thread per (patch row, c*14+kh): 14 contiguous pixels = 28 bytes = 7 x 4-byte words
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 256 * 42;
+  if (idx >= total) return;
+  const int seg = static_cast<int>(idx % 42);
+  const long long row = idx / 42;
+  const int p = static_cast<int>(row % 256);
+  const int b = static_cast<int>(row / 256);
+  const int c = seg / 14, kh = seg % 14;
+  const int ph = p / GRID_P, pw = p % GRID_P;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(
+      px + ((static_cast<size_t>(b) * 3 + c) * IMG + ph * PATCH + kh) * IMG + pw * PATCH);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(cols + static_cast<size_t>(row) * ldk + seg * PATCH);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) dst[i] = __ldg(src + i);
+  if (seg == 41) {
+    __nv_bfloat16* tail = cols + static_cast<size_t>(row) * ldk;
+    for (int k = KREAL; k < ldk; ++k) tail[k] = __float2bfloat16(0.f);
+  }
+}
+
+int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int ldk, cudaStream_t stream) {
+  if (pixels == nullptr || cols == nullptr || B <= 0) return BLB_ERR_ARG;
+  if (ldk < KREAL || ldk % 8 != 0) return BLB_ERR_SHAPE;
+  const long long total = static_cast<long long>(B) * 256 * 42;
+  im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pixels, cols, B, ldk);
+  count_launch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+__global__ void prefix_kernel(const float* __restrict__ prefix, float* __restrict__ resid, int T, int n_prefix,
+                              int D) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < n_prefix * D; i += blockDim.x)
+    resid[static_cast<size_t>(b) * T * D + i] = prefix[i];
+}
+
+int write_prefix_tokens(const float* prefix, float* resid, int B, int T, int n_prefix, int D, cudaStream_t stream) {
+  if (n_prefix == 0) return 0;
+  if (prefix == nullptr || resid == nullptr || B <= 0 || n_prefix > T) return BLB_ERR_ARG;
+  prefix_kernel<<<B, 256, 0, stream>>>(prefix, resid, T, n_prefix, D);
+  count_launch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace blb

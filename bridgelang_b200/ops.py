@@ -1,0 +1,143 @@
+"""ops.py — torch-tensor front ends for the primitive C-ABI operators.
+
+PyTorch is plumbing here (device memory + the current stream); every function hands raw pointers to
+libbridgelang_b200.so and raises if the tensors are not CUDA tensors — there is no eager fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_PATCH, EPI_RESIDUAL, Epilogue  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("bridgelang_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, resid=None, out=None,
+         out_col_off: int = 0, pos=None, tok_in: int = 0, tok_out: int = 0, tok_shift: int = 0) -> Optional[torch.Tensor]:
+    """C = a[M,K] @ w[N,K]^T with the fused epilogue `mode` (see include/bridgelang_b200.h)."""
+    _need_cuda(a, w, bias, gamma, resid, out, pos)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if mode in (EPI_BIAS, EPI_BIAS_GELU) and out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    e = Epilogue()
+    e.bias, e.gamma, e.resid, e.pos = _ptr(bias), _ptr(gamma), _ptr(resid), _ptr(pos)
+    e.ld_resid = resid.stride(0) if resid is not None else 0
+    e.out = _ptr(out)
+    e.ld_out = out.stride(0) if out is not None else 0
+    e.out_col_off = out_col_off
+    e.tok_in, e.tok_out, e.tok_shift = tok_in, tok_out, tok_shift
+    lib = _lib.load()
+    _lib.check(lib.blb_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, mode, C.byref(e),
+                                 _stream()), "gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    _need_cuda(x, weight, bias)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().blb_layernorm(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
+                                         y.stride(0), x.shape[0], x.shape[1], eps, _stream()), "layernorm")
+    return y
+
+
+def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: int) -> torch.Tensor:
+    """qkv: bf16 [batch*tokens, 3*heads*head_dim] (timm packing) → bf16 [batch*tokens, heads*head_dim]."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (batch * tokens, 3 * heads * head_dim)
+    out = torch.empty((batch * tokens, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().blb_attention(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, head_dim, _stream()),
+               "attention")
+    return out
+
+
+def im2col_patch14(pixels: torch.Tensor, ldk: int = 592) -> torch.Tensor:
+    _need_cuda(pixels)
+    assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.shape[1:] == (3, 224, 224)
+    B = pixels.shape[0]
+    cols = torch.empty((B * 256, ldk), dtype=torch.bfloat16, device=pixels.device)
+    _lib.check(_lib.load().blb_im2col_patch14(pixels.data_ptr(), cols.data_ptr(), B, ldk, _stream()), "im2col")
+    return cols
+
+
+_DTYPES = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16}
+
+
+def argmax(logits: torch.Tensor) -> torch.Tensor:
+    """torch.argmax(logits, dim=-1) for a 2-D [rows, vocab] tensor, on the device, int64."""
+    _need_cuda(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in _DTYPES
+    ids = torch.empty((logits.shape[0],), dtype=torch.int64, device=logits.device)
+    _lib.check(_lib.load().blb_argmax(logits.data_ptr(), _DTYPES[logits.dtype], logits.shape[0], logits.shape[1],
+                                      logits.stride(0), ids.data_ptr(), _stream()), "argmax")
+    return ids
+
+
+class DecodeTables:
+    """Device copies of bin_centers and the q01/q99/mask statistics of one dataset."""
+
+    def __init__(self, bin_centers: np.ndarray, q01=None, q99=None, mask=None, device="cuda") -> None:
+        self.bin_centers = torch.from_numpy(np.ascontiguousarray(bin_centers, dtype=np.float64)).to(device)
+        self.q01 = None if q01 is None else torch.tensor(np.asarray(q01, dtype=np.float64), device=device)
+        self.q99 = None if q99 is None else torch.tensor(np.asarray(q99, dtype=np.float64), device=device)
+        self.mask = None if mask is None else torch.tensor(np.asarray(mask, dtype=bool), device=device).to(torch.uint8)
+        self.action_dim = 0 if q01 is None else int(len(q01))
+
+
+def detokenize_unnormalize(ids: torch.Tensor, vocab_size: int, tables: DecodeTables):
+    """ids int64 [n] → (normalized float64 [n], actions float64 [n]); bit-exact vs the NumPy reference."""
+    _need_cuda(ids)
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    n = ids.numel()
+    norm = torch.empty((n,), dtype=torch.float64, device=ids.device)
+    act = torch.empty((n,), dtype=torch.float64, device=ids.device)
+    _lib.check(_lib.load().blb_detokenize_unnormalize(
+        ids.data_ptr(), n, vocab_size, tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim,
+        _ptr(tables.q01), _ptr(tables.q99), _ptr(tables.mask), norm.data_ptr(), act.data_ptr(), _stream()),
+        "detokenize_unnormalize")
+    return norm, act
+
+
+def argmax_detokenize_unnormalize(logits: torch.Tensor, vocab_size: int, tables: DecodeTables):
+    """One launch: full-row argmax → bin centre → un-normalize.  Returns (ids, normalized, actions)."""
+    _need_cuda(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in _DTYPES
+    rows = logits.shape[0]
+    ids = torch.empty((rows,), dtype=torch.int64, device=logits.device)
+    norm = torch.empty((rows,), dtype=torch.float64, device=logits.device)
+    act = torch.empty((rows,), dtype=torch.float64, device=logits.device)
+    _lib.check(_lib.load().blb_argmax_detokenize_unnormalize(
+        logits.data_ptr(), _DTYPES[logits.dtype], rows, logits.shape[1], logits.stride(0), vocab_size,
+        tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim, _ptr(tables.q01),
+        _ptr(tables.q99), _ptr(tables.mask), ids.data_ptr(), norm.data_ptr(), act.data_ptr(), _stream()),
+        "argmax_detokenize_unnormalize")
+    return ids, norm, act
+
+
+def launch_count() -> int:
+    return int(_lib.load().blb_launch_count())
+
+
+def set_gemm_cta_group(ctas: int) -> None:
+    _lib.load().blb_set_gemm_cta_group(int(ctas))

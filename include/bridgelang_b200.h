@@ -1,0 +1,162 @@
+/* bridgelang_b200.h — C ABI of libbridgelang_b200.so: the B200-native (sm_100a) visual-prefix hot path of
+ * OpenVLA / prismatic as found in CliffKai/BridgeLang.
+ *
+ * The reference has NO native layer: its boundary for this path is a set of Python classes
+ * (SURVEY.md §8b).  Each entry point below names the reference interface whose device work it replaces;
+ * the Python mirrors of those classes live in bridgelang_b200/*.py and bind these symbols with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); nothing synchronises;
+ *   - return value: 0 = ok, < 0 = bad argument (BLB_ERR_*), > 0 = cudaError_t of the failed runtime call;
+ *   - never throws; callers own all memory (PyTorch tensors on the reference side);
+ *   - bf16 activations/weights, fp32 biases / LayerNorm / LayerScale parameters and fp32 residual stream.
+ */
+#ifndef BRIDGELANG_B200_H_
+#define BRIDGELANG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLB_OK 0
+#define BLB_ERR_ARG (-1)       /* null pointer / non-positive size */
+#define BLB_ERR_SHAPE (-2)     /* shape unsupported by the tiling (N %% 128, head_dim not in {64,72}, ...) */
+#define BLB_ERR_ALIGN (-3)     /* pointer or row pitch not 16-byte aligned */
+#define BLB_ERR_DRIVER (-4)    /* cuTensorMapEncodeTiled unavailable / failed */
+#define BLB_ERR_WORKSPACE (-5) /* workspace too small */
+
+/* GEMM epilogue modes */
+#define BLB_EPI_BIAS 0      /* out_bf16 = acc + bias                                   (Attention.qkv, projector fc3) */
+#define BLB_EPI_BIAS_GELU 1 /* out_bf16 = gelu_erf(acc + bias)                         (Mlp.fc1+GELU, projector fc1/fc2) */
+#define BLB_EPI_RESIDUAL 2  /* resid_f32 += gamma*(acc+bias) [+ bf16 copy, row-remapped] (Attention.proj / Mlp.fc2 + LayerScale + add) */
+#define BLB_EPI_PATCH 3     /* resid_f32[remap(row)] = acc + bias + pos[token]          (PatchEmbed + _pos_embed) */
+
+/* logits dtypes for the decode tail */
+#define BLB_DTYPE_F32 0
+#define BLB_DTYPE_BF16 1
+#define BLB_DTYPE_F16 2
+
+typedef struct blb_epilogue {
+  const float* bias;   /* [N] or NULL */
+  const float* gamma;  /* [N] LayerScale or NULL (= 1) */
+  float* resid;        /* fp32 residual stream [M, ld_resid] */
+  int32_t ld_resid;
+  void* out;           /* bf16 destination */
+  int32_t ld_out;
+  int32_t out_col_off;
+  const float* pos;    /* [tok_in, N] position embedding (BLB_EPI_PATCH) */
+  int32_t tok_in;      /* row remap per image: src row b*tok_in+t -> dst row b*tok_out+t+tok_shift; 0 = identity */
+  int32_t tok_out;
+  int32_t tok_shift;
+} blb_epilogue;
+
+/* One timm `Block` (vision_transformer.Block as instantiated at dinosiglip_vit.py:50-58). */
+typedef struct blb_block_weights {
+  const float* ln1_w; const float* ln1_b;       /* norm1 [D] */
+  const void* qkv_w;  const float* qkv_b;       /* attn.qkv  bf16 [3D, D], fp32 [3D] */
+  const void* proj_w; const float* proj_b;      /* attn.proj bf16 [D, D],  fp32 [D] */
+  const float* ls1;                             /* ls1.gamma / scale_factor [D] or NULL (SigLIP) */
+  const float* ln2_w; const float* ln2_b;       /* norm2 [D] */
+  const void* fc1_w;  const float* fc1_b;       /* mlp.fc1 bf16 [Hm_pad, D], fp32 [Hm_pad] (rows >= Hm zero) */
+  const void* fc2_w;  const float* fc2_b;       /* mlp.fc2 bf16 [D, Hm_pad] (cols >= Hm zero), fp32 [D] */
+  const float* ls2;                             /* ls2.gamma or NULL */
+} blb_block_weights;
+
+/* One timm VisionTransformer restricted to what get_intermediate_layers(n={depth-2}) needs. */
+typedef struct blb_vit_weights {
+  int32_t dim;        /* D: 1024 (DINOv2 ViT-L/14-reg4) / 1152 (SigLIP SO400M/14) */
+  int32_t heads;      /* 16 */
+  int32_t head_dim;   /* 64 / 72 */
+  int32_t hidden_pad; /* MLP hidden padded to a multiple of 256: 4096 / 4352 (from 4304) */
+  int32_t n_prefix;   /* 5 (cls + 4 reg) / 0 */
+  int32_t n_blocks;   /* blocks to run = depth - 1 (23 / 26): output of block depth-2, final norm NOT applied */
+  int32_t patch_ldk;  /* row pitch of patch_w: 592 (588 padded to 16 B) */
+  float ln_eps;       /* 1e-6 */
+  const void* patch_w;       /* patch_embed.proj.weight as bf16 [D, patch_ldk], k = c*196 + kh*14 + kw */
+  const float* patch_b;      /* [D] */
+  const float* pos_embed;    /* [256, D] */
+  const float* prefix;       /* [n_prefix, D]: cls_token then reg_token rows, or NULL */
+  const blb_block_weights* blocks_host; /* HOST array of n_blocks entries (device pointers inside) */
+} blb_vit_weights;
+
+/* prismatic/util/nn_utils.py:37-53 FusedMLPProjector == extern/hf/modeling_prismatic.py:146-158 fc1/fc2/fc3 */
+typedef struct blb_projector_weights {
+  int32_t in_dim;      /* 2176 */
+  int32_t hidden_dim;  /* 8704 = 4 * in_dim */
+  int32_t out_dim;     /* 4096 (llm_dim) */
+  const void* fc1_w; const float* fc1_b;  /* bf16 [hidden, in] */
+  const void* fc2_w; const float* fc2_b;  /* bf16 [out, hidden] */
+  const void* fc3_w; const float* fc3_b;  /* bf16 [out, out] */
+} blb_projector_weights;
+
+/* ---- library info ------------------------------------------------------------------------------------- */
+int blb_abi_version(void);
+const char* blb_status_string(int status);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+long long blb_launch_count(void);
+/* 0 = auto, 1 = cta_group::1 tiles (128xBN), 2 = cta_group::2 CTA pairs (256xBN) */
+void blb_set_gemm_cta_group(int ctas);
+
+/* ---- primitive operators (each replaces one library call of the reference; used by the parity tests) --- */
+/* C = A[M,K] (bf16, pitch lda) x W[N,K]^T (bf16, pitch ldw) with a fused epilogue.
+ * Replaces nn.Linear (+GELU / +LayerScale+residual) reached via timm Attention/Mlp and nn_utils.py:42-48. */
+int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int mode,
+                  const blb_epilogue* epi, void* stream);
+/* timm LayerNorm(D, eps) on fp32 rows -> bf16 rows (Block.norm1 / norm2). */
+int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void* y_bf16, int ldy, int rows, int D,
+                  float eps, void* stream);
+/* timm Attention core: softmax(q k^T hd^-0.5) v on packed qkv bf16 [B*T, 3*H*hd] -> bf16 [B*T, H*hd]. */
+int blb_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int H, int head_dim, void* stream);
+/* timm PatchEmbed staging: pixels bf16 [B,3,224,224] -> bf16 [B*256, ldk], k = c*196+kh*14+kw, zero padded. */
+int blb_im2col_patch14(const void* pixels_bf16, void* cols_bf16, int B, int ldk, void* stream);
+
+/* ---- towers, projector, fused path ---------------------------------------------------------------------- */
+size_t blb_vit_workspace_bytes(const blb_vit_weights* w, int batch);
+/* timm VisionTransformer.get_intermediate_layers(n={depth-2}) + unpack_tuple (base_vision.py:27-32):
+ * writes patch tokens (prefix dropped) as bf16 into out[b*256+p, out_col_off : out_col_off+D], pitch ld_out. */
+int blb_vit_tower_forward(const blb_vit_weights* w, const void* pixels_bf16, int batch, void* out_bf16, int ld_out,
+                          int out_col_off, void* workspace, size_t workspace_bytes, void* stream);
+
+size_t blb_projector_workspace_bytes(const blb_projector_weights* w, int rows);
+/* FusedMLPProjector.forward (nn_utils.py:52-53): x bf16 [rows, in_dim] -> out bf16.
+ * tok_in/tok_out/tok_shift (0,0,0 = plain [rows, out_dim]) let fc3 store straight into an
+ * inputs_embeds buffer [B, tok_out, out_dim] at token offset tok_shift (prismatic.py:389-396 splice). */
+int blb_projector_forward(const blb_projector_weights* w, const void* x_bf16, int ldx, int rows, void* out_bf16,
+                          int ld_out, int tok_in, int tok_out, int tok_shift, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+size_t blb_fused_workspace_bytes(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                 const blb_projector_weights* proj, int batch);
+/* DinoSigLIPViTBackbone.forward (dinosiglip_vit.py:142-147) [+ projector when proj != NULL].
+ * pixels_*: bf16 [batch,3,224,224] per tower (the dict of dinosiglip_vit.py:39-40; HF packs them as
+ * [batch,6,224,224], modeling_prismatic.py:120).  features_bf16 [batch*256, 2176] is always written;
+ * projected_bf16 [batch*256, out_dim] when proj != NULL. */
+int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                        const blb_projector_weights* proj, const void* pixels_dino,
+                                        const void* pixels_siglip, int batch, void* features_bf16,
+                                        void* projected_bf16, void* workspace, size_t workspace_bytes,
+                                        void* stream);
+
+/* ---- decode tail ---------------------------------------------------------------------------------------- */
+/* torch.argmax over each full logits row (first max wins; NaN maximal) -> int64 ids. */
+int blb_argmax(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, void* stream);
+/* ActionTokenizer.decode_token_ids_to_actions (action_tokenizer.py:65-68) + un-normalize (openvla.py:94-101).
+ * stats index = j %% action_dim; q01/q99/mask may be NULL (then actions == normalized). float64 bit-exact. */
+int blb_detokenize_unnormalize(const int64_t* ids, int n, int vocab_size, const double* bin_centers, int n_centers,
+                               int action_dim, const double* q01, const double* q99, const uint8_t* mask,
+                               double* normalized_out, double* actions_out, void* stream);
+/* both of the above in one launch: row r of logits is decode step r. */
+int blb_argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int vocab_size,
+                                      const double* bin_centers, int n_centers, int action_dim, const double* q01,
+                                      const double* q99, const uint8_t* mask, int64_t* ids, double* normalized_out,
+                                      double* actions_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIDGELANG_B200_H_ */

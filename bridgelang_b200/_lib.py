@@ -56,6 +56,9 @@ _SIGNATURES = {
     "blb_status_string": (C.c_char_p, [C.c_int]),
     "blb_launch_count": (C.c_longlong, []),
     "blb_set_gemm_cta_group": (None, [C.c_int]),
+    "blb_timing_enable": (None, [C.c_int]),
+    "blb_timing_reset": (None, []),
+    "blb_timing_collect": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "blb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(Epilogue), C.c_void_p]),
     "blb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

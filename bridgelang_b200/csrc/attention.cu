@@ -208,6 +208,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
     configured_smem = smem;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T) * T * HD, stream);
   kern<<<B * H, 128, smem, stream>>>(qkv, out, T, H, scale_log2);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());

@@ -188,6 +188,12 @@ const char* blb_status_string(int status) {
 
 long long blb_launch_count(void) { return launch_count(); }
 void blb_set_gemm_cta_group(int ctas) { gemm_set_cta_group(ctas); }
+void blb_timing_enable(int on) { timing_enable(on); }
+void blb_timing_reset(void) { timing_reset(); }
+int blb_timing_collect(int category, double* ms, double* work, long long* launches) {
+  if (category < 0 || category >= TIME_NCAT) return BLB_ERR_ARG;
+  return timing_collect(category, ms, work, launches);
+}
 
 int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int mode,
                   const blb_epilogue* epi, void* stream) {

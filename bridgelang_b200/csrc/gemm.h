@@ -38,6 +38,21 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
 void gemm_set_cta_group(int ctas);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int num_sms();
+
+// Optional per-launch device timing (bench.py's roofline): when enabled, every kernel launch is bracketed by a
+// pair of CUDA events on its own stream; timing_collect() sums them per category after the caller synchronised.
+enum TimingCategory : int { TIME_GEMM = 0, TIME_ATTENTION = 1, TIME_LAYERNORM = 2, TIME_OTHER = 3, TIME_NCAT = 4 };
+void timing_enable(int on);
+bool timing_enabled();
+void timing_begin(cudaStream_t s);
+void timing_end(int cat, double work, cudaStream_t s);
+int timing_collect(int cat, double* ms, double* work, long long* launches);
+void timing_reset();
+struct TimingScope {
+  int cat; double work; cudaStream_t s; bool on;
+  TimingScope(int c, double w, cudaStream_t st) : cat(c), work(w), s(st), on(timing_enabled()) { if (on) timing_begin(s); }
+  ~TimingScope() { if (on) timing_end(cat, work, s); }
+};
 long long launch_count();
 void count_launch(int n);
 

@@ -14,6 +14,8 @@
 //   warp 3      idle
 //   warps 4-11  epilogue       (tcgen05.ld → registers → fused bias/GELU/LayerScale/residual → global)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <vector>
+
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -331,6 +333,46 @@ static int g_force_ctas = 0;   // 0 = auto, 1 / 2 = forced (tests and A/B measur
 static long long g_launches = 0;
 
 void gemm_set_cta_group(int ctas) { g_force_ctas = ctas; }
+
+// ---- optional per-launch timing ------------------------------------------------------------------
+namespace {
+struct TimingRec { int cat; double work; cudaEvent_t e0, e1; };
+bool g_timing = false;
+std::vector<TimingRec> g_recs;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t g_pending_e0 = nullptr;
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+void timing_enable(int on) { g_timing = on != 0; }
+bool timing_enabled() { return g_timing; }
+void timing_begin(cudaStream_t s) { g_pending_e0 = get_event(); cudaEventRecord(g_pending_e0, s); }
+void timing_end(int cat, double work, cudaStream_t s) {
+  cudaEvent_t e1 = get_event();
+  cudaEventRecord(e1, s);
+  g_recs.push_back({cat, work, g_pending_e0, e1});
+  g_pending_e0 = nullptr;
+}
+void timing_reset() {
+  for (auto& r : g_recs) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
+  g_recs.clear();
+}
+int timing_collect(int cat, double* ms, double* work, long long* launches) {
+  double t = 0, w = 0; long long n = 0;
+  for (auto& r : g_recs) {
+    if (r.cat != cat) continue;
+    float f = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&f, r.e0, r.e1);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    t += f; w += r.work; ++n;
+  }
+  if (ms) *ms = t;
+  if (work) *work = w;
+  if (launches) *launches = n;
+  return 0;
+}
 long long launch_count() { return g_launches; }
 void count_launch(int n) { g_launches += n; }
 
@@ -371,6 +413,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  TimingScope ts(TIME_GEMM, 2.0 * M * N * K, stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, epi);
   count_launch(1);
   return static_cast<int>(e);

@@ -55,6 +55,7 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
   if (x == nullptr || w == nullptr || b == nullptr || y == nullptr || rows <= 0) return BLB_ERR_ARG;
   if (D % 128 != 0 || D > 2048 || ldx % 4 != 0 || ldy % 4 != 0) return BLB_ERR_SHAPE;
   const dim3 grid((rows + 7) / 8), block(256);
+  TimingScope ts(TIME_LAYERNORM, 6.0 * rows * D, stream);   // bytes: fp32 read + bf16 write
   switch (D / 128) {
 #define BLB_LN_CASE(V) \
   case V: layernorm_kernel<V><<<grid, block, 0, stream>>>(x, ldx, w, b, y, ldy, rows, eps); break;

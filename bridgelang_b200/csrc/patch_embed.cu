@@ -42,6 +42,7 @@ int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int 
   if (pixels == nullptr || cols == nullptr || B <= 0) return BLB_ERR_ARG;
   if (ldk < KREAL || ldk % 8 != 0) return BLB_ERR_SHAPE;
   const long long total = static_cast<long long>(B) * 256 * 42;
+  TimingScope ts(TIME_OTHER, 4.0 * B * 256 * 588, stream);
   im2col_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pixels, cols, B, ldk);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());

@@ -16,6 +16,23 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_PATCH, EPI_RESIDUAL, Epilogue  # noqa: F401
 
 
+_WORKSPACES: dict = {}
+
+
+def shared_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """One grow-only scratch buffer per (device, stream): towers and the projector run back to back on a stream,
+    so they can share it (their lifetimes never overlap); different streams get different buffers."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _WORKSPACES.pop(key, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -141,3 +158,26 @@ def launch_count() -> int:
 
 def set_gemm_cta_group(ctas: int) -> None:
     _lib.load().blb_set_gemm_cta_group(int(ctas))
+
+
+TIMING_CATEGORIES = ("gemm", "attention", "layernorm", "other")
+
+
+def timing_enable(on: bool) -> None:
+    _lib.load().blb_timing_enable(1 if on else 0)
+
+
+def timing_reset() -> None:
+    _lib.load().blb_timing_reset()
+
+
+def timing_collect() -> dict:
+    """{category: {"ms", "work", "launches"}} summed over every launch recorded since the last reset.
+    Call after torch.cuda.synchronize()."""
+    lib = _lib.load()
+    out = {}
+    for i, name in enumerate(TIMING_CATEGORIES):
+        ms, work, n = C.c_double(), C.c_double(), C.c_longlong()
+        _lib.check(lib.blb_timing_collect(i, C.byref(ms), C.byref(work), C.byref(n)), "timing_collect")
+        out[name] = {"ms": ms.value, "work": work.value, "launches": n.value}
+    return out

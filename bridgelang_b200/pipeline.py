@@ -1,0 +1,106 @@
+"""pipeline.py — the fused featurize+project call and its data-parallel sharding.
+
+`VisualPrefixEncoder` is what `PrismaticVLM.forward` does at prismatic/models/vlms/prismatic.py:367-375
+(`vision_backbone(pixel_values)` then `projector(...)`) as ONE C-ABI call
+(`blb_fused_featurize_project_forward`): DINOv2 tower → SigLIP tower → 3-GEMM projector, sharing one workspace.
+
+Multi-GPU: every image is independent, so the path shards by image batch — one process per GPU,
+weights replicated, contiguous image slices per rank and NO collective inside the path.  The only exchange is the
+optional re-assembly of projected prefixes when the LLM runs on fewer ranks: an NCCL all-gather over NVLink
+(`gather_prefixes`; gloo on CPU for the host-logic tests).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib, ops
+from .config import NUM_PATCHES
+from .projector import FusedMLPProjector, PrismaticProjector
+from .vision import DinoSigLIPViTBackbone, PrismaticVisionBackbone, _as_pixels
+
+
+class VisualPrefixEncoder(nn.Module):
+    """pixel_values {"dino","siglip"} (or HF-packed [B,6,224,224]) → projected prefix [B, 256, llm_dim] bf16."""
+
+    def __init__(self, vision_backbone: nn.Module, projector: nn.Module) -> None:
+        super().__init__()
+        self.vision_backbone = vision_backbone
+        self.projector = projector
+        if isinstance(vision_backbone, DinoSigLIPViTBackbone):
+            self._towers = (vision_backbone.dino_featurizer, vision_backbone.siglip_featurizer)
+        elif isinstance(vision_backbone, PrismaticVisionBackbone) and vision_backbone.use_fused_vision_backbone:
+            self._towers = (vision_backbone.featurizer, vision_backbone.fused_featurizer)
+        else:
+            raise ValueError("VisualPrefixEncoder needs a fused DINOv2+SigLIP backbone")
+        if not isinstance(projector, (FusedMLPProjector, PrismaticProjector)):
+            raise ValueError("VisualPrefixEncoder needs a FusedMLPProjector / PrismaticProjector")
+
+    @staticmethod
+    def _split(pixel_values) -> Tuple[torch.Tensor, torch.Tensor]:
+        if isinstance(pixel_values, dict):
+            return pixel_values["dino"], pixel_values["siglip"]
+        img, img_fused = torch.split(pixel_values, [3, 3], dim=1)   # modeling_prismatic.py:120
+        return img, img_fused
+
+    @torch.no_grad()
+    def forward(self, pixel_values, return_features: bool = False):
+        dino_px, siglip_px = self._split(pixel_values)
+        dino_px, siglip_px = _as_pixels(dino_px), _as_pixels(siglip_px)
+        B, dev = dino_px.shape[0], dino_px.device
+        lib = _lib.load()
+        dino, siglip = self._towers[0].packed(), self._towers[1].packed()
+        proj = self.projector.packed()
+        fused_dim = dino.struct.dim + siglip.struct.dim
+        feats = torch.empty((B, NUM_PATCHES, fused_dim), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((B, NUM_PATCHES, proj.out_dim), dtype=torch.bfloat16, device=dev)
+        need = lib.blb_fused_workspace_bytes(C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), B)
+        ws = ops.shared_workspace(dev, need)
+        _lib.check(lib.blb_fused_featurize_project_forward(
+            C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), dino_px.data_ptr(), siglip_px.data_ptr(), B,
+            feats.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+            "fused_featurize_project_forward")
+        return (out, feats) if return_features else out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# data-parallel sharding
+# ----------------------------------------------------------------------------------------------------------
+def shard_bounds(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous image slice [lo, hi) of rank `rank`; the first (global_batch % world_size) ranks get one more."""
+    if world_size <= 0 or not (0 <= rank < world_size) or global_batch < 0:
+        raise ValueError("bad shard request")
+    base, extra = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_pixel_values(pixel_values: Dict[str, torch.Tensor], rank: int, world_size: int) -> Dict[str, torch.Tensor]:
+    n = next(iter(pixel_values.values())).shape[0]
+    lo, hi = shard_bounds(n, rank, world_size)
+    return {k: v[lo:hi] for k, v in pixel_values.items()}
+
+
+def gather_prefixes(local: torch.Tensor, global_batch: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather the per-rank projected prefixes [B_local, 256, llm_dim] into [global_batch, 256, llm_dim] on
+    every rank (NCCL over NVLink on GPUs).  Uneven shards are padded to the largest shard for the collective."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
+    max_n = max(hi - lo for lo, hi in sizes)
+    lo, hi = sizes[rank]
+    assert local.shape[0] == hi - lo, "local shard does not match shard_bounds()"
+    if local.shape[0] < max_n:
+        pad = torch.zeros((max_n - local.shape[0], *local.shape[1:]), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], dim=0)
+    gathered = torch.empty((world * max_n, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    if all(h - l == max_n for l, h in sizes):
+        return gathered
+    parts: List[torch.Tensor] = [gathered[r * max_n: r * max_n + (h - l)] for r, (l, h) in enumerate(sizes)]
+    return torch.cat(parts, dim=0)

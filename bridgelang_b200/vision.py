@@ -1,0 +1,488 @@
+"""vision.py — B200-native mirrors of the reference's vision-backbone classes for `prism-dinosiglip-224px`.
+
+  VisionBackbone / DinoSigLIPViTBackbone   prismatic/models/backbones/vision/base_vision.py:54-90,
+                                           prismatic/models/backbones/vision/dinosiglip_vit.py:43-163
+  PrismaticVisionBackbone (HF twin)        prismatic/extern/hf/modeling_prismatic.py:63-123
+  SigLIPViTBackbone / DinoV2ViTBackbone    prismatic/models/backbones/vision/{siglip_vit,dinov2_vit}.py
+
+Same constructor arguments, attributes, state-dict key names (timm's) and forward contracts as the reference, so
+reference checkpoints load with `load_state_dict` and callers (`PrismaticVLM.forward`, prismatic.py:367-375) do not
+change.  The arithmetic is NOT timm/PyTorch: `forward` hands raw device pointers to libbridgelang_b200.so
+(hand-written sm_100a kernels).  Inference only (the reference's `freeze_vision_backbone` stages and every
+`predict_action` use); there is no eager/CPU fallback — a missing library or a CPU tensor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from functools import partial
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .config import (DINOV2_L14_REG4, LN_EPS, NUM_PATCHES, PATCH, PATCH_K, PATCH_LDK, SIGLIP_SO400M_14, VitConfig)
+from .weights import DINO_MEAN, DINO_STD, SIGLIP_MEAN, SIGLIP_STD
+
+# Registry =>> same ids as dinosiglip_vit.py:21-30 / siglip_vit.py:8-13 / dinov2_vit.py:9-10 (224 px members)
+DINOSigLIP_VISION_BACKBONES = {
+    "dinosiglip-vit-so-224px": {"dino": DINOV2_L14_REG4, "siglip": SIGLIP_SO400M_14},
+}
+SIGLIP_VISION_BACKBONES = {"siglip-vit-so400m": SIGLIP_SO400M_14}
+DINOv2_VISION_BACKBONES = {"dinov2-vit-l": DINOV2_L14_REG4}
+TIMM_ID_TO_CONFIG = {c.timm_id: c for c in (DINOV2_L14_REG4, SIGLIP_SO400M_14)}
+
+
+def unpack_tuple(fn: Callable[[Any], Tuple[Any]]) -> Callable[[Any], Any]:
+    """base_vision.py:27-32 (kept for API parity; the native towers return a tensor already)."""
+    def wrapper(*args: Any, **kwargs: Any) -> Any:
+        result = fn(*args, **kwargs)
+        return result[0] if isinstance(result, tuple) else result
+
+    return wrapper
+
+
+# ======================================================================================================
+# Parameter containers with timm's module tree (names only — no timm code runs)
+# ======================================================================================================
+class LayerScale(nn.Module):
+    """timm LayerScale: holds `gamma` (or `scale_factor` in the HF twin, modeling_prismatic.py:52-59)."""
+
+    def __init__(self, dim: int, init_values: float = 1e-5, param_name: str = "gamma") -> None:
+        super().__init__()
+        self.param_name = param_name
+        setattr(self, param_name, nn.Parameter(init_values * torch.ones(dim)))
+
+    @property
+    def value(self) -> torch.Tensor:
+        return getattr(self, self.param_name)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):  # accept either spelling
+        other = "scale_factor" if self.param_name == "gamma" else "gamma"
+        if prefix + other in state_dict and prefix + self.param_name not in state_dict:
+            state_dict[prefix + self.param_name] = state_dict.pop(prefix + other)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim, bias=True)
+        self.proj = nn.Linear(dim, dim, bias=True)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim: int, hidden: int) -> None:
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden, bias=True)
+        self.fc2 = nn.Linear(hidden, dim, bias=True)
+
+
+class Block(nn.Module):
+    """Parameter holder named like timm.models.vision_transformer.Block (also the FSDP wrap unit)."""
+
+    def __init__(self, cfg: VitConfig, ls_param_name: str) -> None:
+        super().__init__()
+        self.norm1 = nn.LayerNorm(cfg.dim, eps=LN_EPS)
+        self.attn = _Attention(cfg.dim)
+        self.ls1 = LayerScale(cfg.dim, param_name=ls_param_name) if cfg.layer_scale else nn.Identity()
+        self.norm2 = nn.LayerNorm(cfg.dim, eps=LN_EPS)
+        self.mlp = _Mlp(cfg.dim, cfg.mlp_hidden)
+        self.ls2 = LayerScale(cfg.dim, param_name=ls_param_name) if cfg.layer_scale else nn.Identity()
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, kernel_size=PATCH, stride=PATCH, bias=True)
+
+
+class _AttentionPool(nn.Module):
+    """SigLIP's MAP head: present in checkpoints (`attn_pool.*`), never executed on this path (num_classes=0 and
+    get_intermediate_layers bypass it).  Kept so that load_state_dict(strict=True) of reference weights works."""
+
+    def __init__(self, cfg: VitConfig) -> None:
+        super().__init__()
+        D = cfg.dim
+        self.latent = nn.Parameter(torch.zeros(1, 1, D))
+        self.q = nn.Linear(D, D)
+        self.kv = nn.Linear(D, 2 * D)
+        self.proj = nn.Linear(D, D)
+        self.norm = nn.LayerNorm(D, eps=LN_EPS)
+        self.mlp = _Mlp(D, cfg.mlp_hidden)
+
+
+class VisionTransformer(nn.Module):
+    """One tower.  `forward(pixels[B,3,224,224]) -> [B,256,D]` == timm `get_intermediate_layers(n={depth-2})`
+    after `unpack_tuple` (second-to-last block, prefix tokens dropped, final norm not applied)."""
+
+    def __init__(self, cfg: VitConfig, ls_param_name: str = "gamma") -> None:
+        super().__init__()
+        self.cfg = cfg
+        self.embed_dim = cfg.dim
+        D = cfg.dim
+        self.patch_embed = _PatchEmbed(D)
+        if cfg.class_token:
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, D))
+        if cfg.reg_tokens:
+            self.reg_token = nn.Parameter(torch.zeros(1, cfg.reg_tokens, D))
+        self.pos_embed = nn.Parameter(torch.zeros(1, NUM_PATCHES, D))
+        self.blocks = nn.ModuleList([Block(cfg, ls_param_name) for _ in range(cfg.depth)])
+        self.norm = nn.LayerNorm(D, eps=LN_EPS)
+        if cfg.attn_pool:
+            self.attn_pool = _AttentionPool(cfg)
+        self.requires_grad_(False)
+        self.eval()
+        self._packed: Optional[_PackedTower] = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
+
+    # -- packing ------------------------------------------------------------------------------------
+    def invalidate_packed(self) -> None:
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() move the masters → re-pack lazily
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def packed(self) -> "_PackedTower":
+        dev = self.pos_embed.device
+        if dev.type != "cuda":
+            raise RuntimeError("bridgelang_b200 towers run on CUDA only (no CPU fallback): call .cuda() first")
+        if self._packed is None or self._packed.device != dev:
+            self._packed = _PackedTower(self)
+        return self._packed
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        return ops.shared_workspace(self.pos_embed.device, nbytes)
+
+    # -- forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_into(self, pixels: torch.Tensor, out: torch.Tensor, col_off: int) -> None:
+        """Write this tower's patch tokens into out[:, :, col_off:col_off+D] (the fused concat buffer)."""
+        lib = _lib.load()
+        pk = self.packed()
+        B = pixels.shape[0]
+        px = _as_pixels(pixels)
+        need = lib.blb_vit_workspace_bytes(C.byref(pk.struct), B)
+        ws = self.workspace(need)
+        _lib.check(lib.blb_vit_tower_forward(C.byref(pk.struct), px.data_ptr(), B, out.data_ptr(), out.stride(-2),
+                                             col_off, ws.data_ptr(), ws.numel(),
+                                             torch.cuda.current_stream().cuda_stream), "vit_tower_forward")
+
+    def forward(self, pixels: torch.Tensor) -> torch.Tensor:
+        B = pixels.shape[0]
+        out = torch.empty((B, NUM_PATCHES, self.cfg.dim), dtype=torch.bfloat16, device=pixels.device)
+        self.forward_into(pixels, out, 0)
+        return out
+
+    def get_intermediate_layers(self, x: torch.Tensor, n=None, **_: Any) -> Tuple[torch.Tensor]:
+        """timm signature used at dinosiglip_vit.py:61-66; only n = {depth-2} (the reference's choice) exists."""
+        want = {len(self.blocks) - 2}
+        if n is not None and (set(n) if not isinstance(n, int) else {len(self.blocks) - n}) != want:
+            raise ValueError("only the second-to-last block output is available on the native path")
+        return (self.forward(x),)
+
+
+def _as_pixels(pixels: torch.Tensor) -> torch.Tensor:
+    if not pixels.is_cuda:
+        raise RuntimeError("pixel_values must be CUDA tensors (no CPU fallback)")
+    if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, 224, 224):
+        raise ValueError(f"expected pixel_values [B,3,224,224], got {tuple(pixels.shape)}")
+    return pixels.to(torch.bfloat16).contiguous()
+
+
+class _PackedTower:
+    """Device-resident operands in the layout the kernels want: bf16 GEMM weights (fc1/fc2 zero-padded to
+    hidden_pad, patch weight flattened to [D, 592]), fp32 biases / LayerNorm / LayerScale / pos-embed / prefix
+    rows, plus the ctypes descriptor structs.  fp32 masters are rounded to bf16 exactly once, here."""
+
+    def __init__(self, vit: VisionTransformer) -> None:
+        cfg = vit.cfg
+        dev = vit.pos_embed.device
+        self.device = dev
+        self.keep: List[torch.Tensor] = []
+        D, Hm, Hp = cfg.dim, cfg.mlp_hidden, cfg.hidden_pad
+
+        def f32(t: torch.Tensor) -> torch.Tensor:
+            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self.keep.append(t)
+            return t
+
+        def b16(t: torch.Tensor) -> torch.Tensor:
+            t = t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+            self.keep.append(t)
+            return t
+
+        pw = torch.zeros((D, PATCH_LDK), dtype=torch.float32, device=dev)
+        pw[:, :PATCH_K] = vit.patch_embed.proj.weight.detach().reshape(D, PATCH_K).float()   # (c, kh, kw) order
+        prefix = []
+        if cfg.class_token:
+            prefix.append(vit.cls_token.detach().reshape(1, D))
+        if cfg.reg_tokens:
+            prefix.append(vit.reg_token.detach().reshape(cfg.reg_tokens, D))
+        self.prefix = f32(torch.cat(prefix, dim=0)) if prefix else None
+
+        n_blocks = cfg.n_needed_blocks
+        self.blocks = (_lib.BlockWeights * n_blocks)()
+        for i in range(n_blocks):
+            blk: Block = vit.blocks[i]
+            bw = self.blocks[i]
+            fc1_w = torch.zeros((Hp, D), dtype=torch.float32, device=dev)
+            fc1_w[:Hm] = blk.mlp.fc1.weight.detach().float()
+            fc1_b = torch.zeros((Hp,), dtype=torch.float32, device=dev)
+            fc1_b[:Hm] = blk.mlp.fc1.bias.detach().float()
+            fc2_w = torch.zeros((D, Hp), dtype=torch.float32, device=dev)
+            fc2_w[:, :Hm] = blk.mlp.fc2.weight.detach().float()
+            bw.ln1_w, bw.ln1_b = f32(blk.norm1.weight).data_ptr(), f32(blk.norm1.bias).data_ptr()
+            bw.qkv_w, bw.qkv_b = b16(blk.attn.qkv.weight).data_ptr(), f32(blk.attn.qkv.bias).data_ptr()
+            bw.proj_w, bw.proj_b = b16(blk.attn.proj.weight).data_ptr(), f32(blk.attn.proj.bias).data_ptr()
+            bw.ln2_w, bw.ln2_b = f32(blk.norm2.weight).data_ptr(), f32(blk.norm2.bias).data_ptr()
+            bw.fc1_w, bw.fc1_b = b16(fc1_w).data_ptr(), f32(fc1_b).data_ptr()
+            bw.fc2_w, bw.fc2_b = b16(fc2_w).data_ptr(), f32(blk.mlp.fc2.bias).data_ptr()
+            if cfg.layer_scale:
+                bw.ls1, bw.ls2 = f32(blk.ls1.value).data_ptr(), f32(blk.ls2.value).data_ptr()
+            else:
+                bw.ls1, bw.ls2 = None, None
+
+        s = _lib.VitWeights()
+        s.dim, s.heads, s.head_dim, s.hidden_pad = D, cfg.heads, cfg.head_dim, Hp
+        s.n_prefix, s.n_blocks, s.patch_ldk, s.ln_eps = cfg.n_prefix, n_blocks, PATCH_LDK, LN_EPS
+        s.patch_w = b16(pw).data_ptr()
+        s.patch_b = f32(vit.patch_embed.proj.bias).data_ptr()
+        s.pos_embed = f32(vit.pos_embed.reshape(NUM_PATCHES, D)).data_ptr()
+        s.prefix = self.prefix.data_ptr() if self.prefix is not None else None
+        s.blocks_host = C.cast(self.blocks, C.POINTER(_lib.BlockWeights))
+        self.struct = s
+
+
+# ======================================================================================================
+# Image transforms (host side, upstream of the measured path: SURVEY.md §8 a1)
+# ======================================================================================================
+@dataclass
+class LetterboxPad:
+    """base_vision.py:42-51"""
+    padding_fill_value: Tuple[int, int, int]
+
+    def __call__(self, image):
+        import torchvision.transforms.functional as TVF
+        (w, h), max_wh = image.size, max(image.size)
+        horizontal_pad, vertical_pad = int((max_wh - w) / 2), int((max_wh - h) / 2)
+        padding = (horizontal_pad, vertical_pad, horizontal_pad, vertical_pad)
+        return TVF.pad(image, padding, fill=self.padding_fill_value, padding_mode="constant")
+
+
+@dataclass
+class DinoSigLIPImageTransform:
+    """dinosiglip_vit.py:33-40"""
+    dino_image_transform: Callable
+    siglip_image_transform: Callable
+    is_prismatic: bool = True
+
+    def __call__(self, img, **kwargs: str) -> Dict[str, torch.Tensor]:
+        return {"dino": self.dino_image_transform(img, **kwargs), "siglip": self.siglip_image_transform(img, **kwargs)}
+
+
+def _make_transform(strategy: str, size: int, mean, std, *, crop_resize: int):
+    """What timm.data.create_transform(is_training=False) yields for these checkpoints (bicubic Resize →
+    CenterCrop → ToTensor → Normalize), modified per `image_resize_strategy` as dinosiglip_vit.py:82-134 does."""
+    from torchvision import transforms as T
+    from torchvision.transforms import InterpolationMode
+
+    tail = [T.CenterCrop(size), T.ToTensor(), T.Normalize(mean=torch.tensor(mean), std=torch.tensor(std))]
+    if strategy == "resize-naive":
+        return T.Compose([T.Resize((size, size), interpolation=InterpolationMode.BICUBIC), *tail])
+    if strategy == "resize-crop":
+        return T.Compose([T.Resize(crop_resize, interpolation=InterpolationMode.BICUBIC), *tail])
+    if strategy == "letterbox":
+        fill = tuple(int(x * 255) for x in mean)
+        return T.Compose([LetterboxPad(fill), T.Resize(crop_resize, interpolation=InterpolationMode.BICUBIC), *tail])
+    raise ValueError(f"Image Resize Strategy `{strategy}` is not supported!")
+
+
+# ======================================================================================================
+# Reference-facing backbones
+# ======================================================================================================
+class VisionBackbone(nn.Module, ABC):
+    """base_vision.py:54-90, unchanged contract."""
+
+    def __init__(self, vision_backbone_id: str, image_resize_strategy: str, default_image_size: int = 224) -> None:
+        super().__init__()
+        self.identifier: str = vision_backbone_id
+        self.image_resize_strategy: str = image_resize_strategy
+        self.default_image_size: int = default_image_size
+        self.featurizer: nn.Module = None
+        self.image_transform = None
+
+    def get_image_transform(self):
+        return self.image_transform
+
+    @abstractmethod
+    def get_fsdp_wrapping_policy(self) -> Callable: ...
+
+    @abstractmethod
+    def forward(self, pixel_values: torch.Tensor) -> torch.Tensor: ...
+
+    @property
+    @abstractmethod
+    def default_image_resolution(self) -> Tuple[int, int, int]: ...
+
+    @property
+    @abstractmethod
+    def embed_dim(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def num_patches(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def half_precision_dtype(self) -> torch.dtype: ...
+
+
+def _vit_fsdp_policy() -> Callable:
+    from torch.distributed.fsdp.wrap import _module_wrap_policy, _or_policy, transformer_auto_wrap_policy
+    vit_wrap_policy = partial(_module_wrap_policy, module_classes={VisionTransformer})
+    transformer_block_policy = partial(transformer_auto_wrap_policy, transformer_layer_cls={Block})
+    return partial(_or_policy, policies=[vit_wrap_policy, transformer_block_policy])
+
+
+class DinoSigLIPViTBackbone(VisionBackbone):
+    """dinosiglip_vit.py:43-163.  `forward({"dino": [B,3,224,224], "siglip": [B,3,224,224]}) -> [B,256,2176]`
+    (cols 0-1023 DINOv2, 1024-2175 SigLIP).  Each tower's last needed fc2 epilogue writes its column slice of the
+    output directly, so the reference's torch.cat copy does not exist."""
+
+    def __init__(self, vision_backbone_id: str, image_resize_strategy: str, default_image_size: int = 224) -> None:
+        super().__init__(vision_backbone_id, image_resize_strategy, default_image_size=default_image_size)
+        if vision_backbone_id not in DINOSigLIP_VISION_BACKBONES:
+            raise ValueError(f"Vision Backbone `{vision_backbone_id}` is not supported on the B200-native path!")
+        if default_image_size != 224:
+            raise ValueError("the B200-native towers are built for 224 px inputs")
+        cfgs = DINOSigLIP_VISION_BACKBONES[vision_backbone_id]
+        self.dino_timm_path_or_url = cfgs["dino"].timm_id
+        self.siglip_timm_path_or_url = cfgs["siglip"].timm_id
+        self.dino_featurizer = VisionTransformer(cfgs["dino"])
+        self.siglip_featurizer = VisionTransformer(cfgs["siglip"])
+        self.dtype = torch.bfloat16
+        self.dino_data_cfg = {"input_size": (3, 224, 224), "interpolation": "bicubic", "mean": DINO_MEAN,
+                              "std": DINO_STD, "crop_pct": 1.0, "crop_mode": "center"}
+        self.siglip_data_cfg = {"input_size": (3, 224, 224), "interpolation": "bicubic", "mean": SIGLIP_MEAN,
+                                "std": SIGLIP_STD, "crop_pct": 0.9, "crop_mode": "center"}
+        self.image_transform = DinoSigLIPImageTransform(
+            _make_transform(image_resize_strategy, 224, DINO_MEAN, DINO_STD, crop_resize=224),
+            _make_transform(image_resize_strategy, 224, SIGLIP_MEAN, SIGLIP_STD, crop_resize=224),
+        )
+
+    def get_fsdp_wrapping_policy(self) -> Callable:
+        return _vit_fsdp_policy()
+
+    def forward(self, pixel_values: Dict[str, torch.Tensor]) -> torch.Tensor:
+        dino_px, siglip_px = pixel_values["dino"], pixel_values["siglip"]
+        B = dino_px.shape[0]
+        out = torch.empty((B, NUM_PATCHES, self.embed_dim), dtype=torch.bfloat16, device=dino_px.device)
+        self.dino_featurizer.forward_into(dino_px, out, 0)
+        self.siglip_featurizer.forward_into(siglip_px, out, self.dino_featurizer.embed_dim)
+        return out
+
+    @property
+    def default_image_resolution(self) -> Tuple[int, int, int]:
+        return self.dino_data_cfg["input_size"]
+
+    @property
+    def embed_dim(self) -> int:
+        return self.dino_featurizer.embed_dim + self.siglip_featurizer.embed_dim
+
+    @property
+    def num_patches(self) -> int:
+        return NUM_PATCHES
+
+    @property
+    def half_precision_dtype(self) -> torch.dtype:
+        return torch.bfloat16
+
+
+class _SingleTowerBackbone(VisionBackbone):
+    """TimmViTBackbone (base_vision.py:94-207) restricted to the two towers this path owns (BASELINE config 4)."""
+
+    REGISTRY: Dict[str, VitConfig] = {}
+    MEAN: Tuple[float, float, float] = (0.5, 0.5, 0.5)
+    STD: Tuple[float, float, float] = (0.5, 0.5, 0.5)
+
+    def __init__(self, vision_backbone_id: str, image_resize_strategy: str, default_image_size: int = 224) -> None:
+        super().__init__(vision_backbone_id, image_resize_strategy, default_image_size=default_image_size)
+        if vision_backbone_id not in self.REGISTRY:
+            raise ValueError(f"Vision Backbone `{vision_backbone_id}` is not supported on the B200-native path!")
+        cfg = self.REGISTRY[vision_backbone_id]
+        self.timm_path_or_url = cfg.timm_id
+        self.dtype = torch.bfloat16
+        self.featurizer = VisionTransformer(cfg)
+        self.data_cfg = {"input_size": (3, 224, 224), "mean": self.MEAN, "std": self.STD}
+        self.image_transform = _make_transform(image_resize_strategy, 224, self.MEAN, self.STD, crop_resize=224)
+
+    def get_fsdp_wrapping_policy(self) -> Callable:
+        return _vit_fsdp_policy()
+
+    def forward(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        return self.featurizer(pixel_values)
+
+    @property
+    def default_image_resolution(self) -> Tuple[int, int, int]:
+        return self.data_cfg["input_size"]
+
+    @property
+    def embed_dim(self) -> int:
+        return self.featurizer.embed_dim
+
+    @property
+    def num_patches(self) -> int:
+        return NUM_PATCHES
+
+    @property
+    def half_precision_dtype(self) -> torch.dtype:
+        return self.dtype
+
+
+class SigLIPViTBackbone(_SingleTowerBackbone):
+    """siglip_vit.py:8-24 (`siglip-vit-so400m`)."""
+    REGISTRY = SIGLIP_VISION_BACKBONES
+    MEAN, STD = SIGLIP_MEAN, SIGLIP_STD
+
+
+class DinoV2ViTBackbone(_SingleTowerBackbone):
+    """dinov2_vit.py:9-19 (`dinov2-vit-l`)."""
+    REGISTRY = DINOv2_VISION_BACKBONES
+    MEAN, STD = DINO_MEAN, DINO_STD
+
+
+class PrismaticVisionBackbone(nn.Module):
+    """HF twin, modeling_prismatic.py:63-123: attrs `featurizer`, `fused_featurizer`, `embed_dim`;
+    `forward(pixel_values[B,6,224,224])` (dino channels first); LayerScale parameter named `scale_factor`."""
+
+    def __init__(self, use_fused_vision_backbone: bool, image_sizes: List[int], timm_model_ids: List[str],
+                 timm_override_act_layers: List[Optional[str]]) -> None:
+        super().__init__()
+        self.use_fused_vision_backbone = use_fused_vision_backbone
+        assert len(timm_model_ids) <= 2, "Prismatic models only support up to 2 (fused) vision backbones!"
+        if any(s != 224 for s in image_sizes) or any(a is not None for a in timm_override_act_layers):
+            raise ValueError("the B200-native towers support 224 px inputs and timm's default (erf GELU) activation")
+        for tid in timm_model_ids:
+            if tid not in TIMM_ID_TO_CONFIG:
+                raise ValueError(f"timm model `{tid}` is not supported on the B200-native path")
+        self.featurizer = VisionTransformer(TIMM_ID_TO_CONFIG[timm_model_ids[0]], ls_param_name="scale_factor")
+        self.embed_dim = self.featurizer.embed_dim
+        if self.use_fused_vision_backbone:
+            self.fused_featurizer = VisionTransformer(TIMM_ID_TO_CONFIG[timm_model_ids[1]],
+                                                      ls_param_name="scale_factor")
+            self.embed_dim += self.fused_featurizer.embed_dim
+
+    def forward(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        if not self.use_fused_vision_backbone:
+            return self.featurizer(pixel_values)
+        img, img_fused = torch.split(pixel_values, [3, 3], dim=1)
+        B = pixel_values.shape[0]
+        out = torch.empty((B, NUM_PATCHES, self.embed_dim), dtype=torch.bfloat16, device=pixel_values.device)
+        self.featurizer.forward_into(img, out, 0)
+        self.fused_featurizer.forward_into(img_fused, out, self.featurizer.embed_dim)
+        return out

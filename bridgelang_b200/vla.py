@@ -1,0 +1,149 @@
+"""vla.py — `OpenVLA.predict_action` with the visual prefix and the decode tail on the B200-native kernels.
+
+Mirrors prismatic/models/vlas/openvla.py:23-131 (native) and the HF twin
+prismatic/extern/hf/modeling_prismatic.py:492-562: same `predict_action(image, instruction, unnorm_key)` contract,
+same assertion messages in `_check_unnorm_key`, same `get_action_dim` / `get_action_stats`.
+
+What changed underneath (and only that):
+  * vision_backbone + projector run as one fused native call and the projector's fc3 epilogue stores the 256
+    prefix rows straight into the LLM's `inputs_embeds` buffer at token offset 1 (the `torch.cat` splice of
+    prismatic.py:389-396 disappears).  The prefix is computed ONCE per action — the fork's demo runs
+    `use_cache=False` (run_openvla_demo.py:43) and re-runs the towers for each of the 7 decode steps.
+  * greedy decoding uses a device argmax over the FULL logits row (first max index wins, like torch.argmax inside
+    transformers' GenerationMixin), and the final ids → bin centres → q01/q99 un-normalize happen in one kernel in
+    float64; a single device→host copy returns the action vector.
+The language model is untouched: any HF-style causal LM (`get_input_embeddings()`, `forward(inputs_embeds=...,
+past_key_values=..., use_cache=True)` → `.logits`, `.past_key_values`) is driven as a black box.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .action_tokenizer import ActionTokenizer
+from .config import NUM_PATCHES
+from .pipeline import VisualPrefixEncoder
+
+
+class PurePromptBuilder:
+    """prismatic/models/backbones/llm/prompting/base_prompter.py:28-75 (`llama2-7b-pure`)."""
+
+    def __init__(self, model_family: str = "openvla", system_prompt: Optional[str] = None) -> None:
+        self.model_family, self.system_prompt = model_family, system_prompt
+        self.bos, self.eos = "<s>", "</s>"
+        self.prompt, self.turn_count = "", 0
+
+    def add_turn(self, role: str, message: str) -> str:
+        assert (role == "human") if (self.turn_count % 2 == 0) else (role == "gpt")
+        message = message.replace("<image>", "").strip()
+        if (self.turn_count % 2) == 0:
+            wrapped = f"In: {message}\nOut: "
+        else:
+            wrapped = f"{message if message != '' else ' '}{self.eos}"
+        self.prompt += wrapped
+        self.turn_count += 1
+        return wrapped
+
+    def get_prompt(self) -> str:
+        return self.prompt.removeprefix(self.bos).rstrip()
+
+
+class OpenVLA(nn.Module):
+    def __init__(self, vision_backbone: nn.Module, projector: nn.Module, llm: nn.Module, tokenizer: Any,
+                 norm_stats: Dict[str, Dict[str, Dict[str, List[float]]]],
+                 action_tokenizer: Optional[ActionTokenizer] = None, empty_token_id: int = 29871) -> None:
+        super().__init__()
+        self.vision_backbone, self.projector, self.llm = vision_backbone, projector, llm
+        self.tokenizer = tokenizer
+        self.norm_stats = norm_stats
+        self.action_tokenizer = action_tokenizer if action_tokenizer is not None else ActionTokenizer(tokenizer)
+        self.prefix_encoder = VisualPrefixEncoder(vision_backbone, projector)
+        self.empty_token_id = empty_token_id
+
+    def get_prompt_builder(self) -> PurePromptBuilder:
+        return PurePromptBuilder("openvla")
+
+    # -- the part of predict_action between the tokenizer and generate() --------------------------------
+    def _prepare_input_ids(self, instruction: str, device: torch.device) -> torch.Tensor:
+        prompt_builder = self.get_prompt_builder()
+        prompt_builder.add_turn(role="human", message=f"What action should the robot take to {instruction.lower()}?")
+        prompt_text = prompt_builder.get_prompt()
+        input_ids = self.tokenizer(prompt_text, truncation=True, return_tensors="pt").input_ids.to(device)
+        if not torch.all(input_ids[:, -1] == self.empty_token_id):   # openvla.py:59-64
+            extra = torch.tensor([[self.empty_token_id]], dtype=torch.long, device=device)
+            input_ids = torch.cat((input_ids, extra), dim=1)
+        return input_ids
+
+    @torch.inference_mode()
+    def generate_action_token_ids(self, input_ids: torch.Tensor, pixel_values, max_new_tokens: int) -> torch.Tensor:
+        """Greedy decode of `max_new_tokens` ids (batch size 1, as modeling_prismatic.py:460-463 requires)."""
+        assert input_ids.shape[0] == 1, "predict_action supports batch size 1 (as the reference does)"
+        emb = self.llm.get_input_embeddings()
+        tok = emb(input_ids)                                              # [1, T, llm_dim]
+        T, dim = tok.shape[1], tok.shape[2]
+        embeds = torch.empty((1, 1 + NUM_PATCHES + (T - 1), dim), dtype=torch.bfloat16, device=tok.device)
+        embeds[:, :1] = tok[:, :1]                                        # <BOS>
+        embeds[:, 1 + NUM_PATCHES:] = tok[:, 1:]
+        # visual prefix, written by fc3's epilogue at token offset 1 (prismatic.py:389-396 splice)
+        feats = self.vision_backbone(pixel_values)
+        self.projector.project(feats, out=embeds, tok_in=NUM_PATCHES, tok_out=embeds.shape[1], tok_shift=1)
+        out = self.llm(inputs_embeds=embeds.to(tok.dtype), use_cache=True)
+        ids: List[torch.Tensor] = []
+        for step in range(max_new_tokens):
+            logits = out.logits[:, -1, :]
+            nxt = ops.argmax(logits if logits.stride(-1) == 1 else logits.contiguous())   # full-row, first max wins
+            ids.append(nxt)
+            if step + 1 < max_new_tokens:
+                out = self.llm(inputs_embeds=emb(nxt.view(1, 1)), past_key_values=out.past_key_values, use_cache=True)
+        return torch.cat(ids)
+
+    @torch.inference_mode()
+    def predict_action(self, image, instruction: str, unnorm_key: Optional[str] = None, **kwargs: str) -> np.ndarray:
+        """PIL image + instruction → un-normalized continuous action, np.float64[action_dim]."""
+        device = next(self.llm.parameters()).device
+        input_ids = self._prepare_input_ids(instruction, device)
+        pixel_values = self.vision_backbone.get_image_transform()(image)
+        if isinstance(pixel_values, torch.Tensor):
+            pixel_values = pixel_values[None, ...].to(device)
+        elif isinstance(pixel_values, dict):
+            pixel_values = {k: v[None, ...].to(device) for k, v in pixel_values.items()}
+        else:
+            raise ValueError(f"Unsupported `pixel_values` type = {type(pixel_values)}")
+        action_dim = self.get_action_dim(unnorm_key)
+        ids = self.generate_action_token_ids(input_ids, pixel_values, action_dim)
+        _, actions = self.action_tokenizer.decode_on_device(ids, self.get_action_stats(unnorm_key))
+        return actions.cpu().numpy()
+
+    # -- openvla.py:105-131, verbatim semantics --------------------------------------------------------
+    @staticmethod
+    def _check_unnorm_key(norm_stats: Dict, unnorm_key: Optional[str]) -> str:
+        if unnorm_key is None:
+            assert len(norm_stats) == 1, (
+                f"Your model was trained on more than one dataset, please pass a `unnorm_key` from the following "
+                f"options to choose the statistics used for un-normalizing actions: {norm_stats.keys()}"
+            )
+            unnorm_key = next(iter(norm_stats.keys()))
+        assert (
+            unnorm_key in norm_stats
+        ), f"The `unnorm_key` you chose is not in the set of available statistics; choose from: {norm_stats.keys()}"
+        return unnorm_key
+
+    def get_action_dim(self, unnorm_key: Optional[str] = None) -> int:
+        unnorm_key = self._check_unnorm_key(self.norm_stats, unnorm_key)
+        return len(self.norm_stats[unnorm_key]["action"]["q01"])
+
+    def get_action_stats(self, unnorm_key: Optional[str] = None) -> Dict:
+        unnorm_key = self._check_unnorm_key(self.norm_stats, unnorm_key)
+        return self.norm_stats[unnorm_key]["action"]
+
+
+def decode_tail_from_logits(logits: torch.Tensor, action_tokenizer: ActionTokenizer, stats: Optional[Dict]):
+    """[steps, vocab_rows] logits → (ids, normalized, actions) in one launch (argmax → de-tokenize → un-normalize).
+    Equivalent to torch.argmax per step followed by openvla.py:89-101 on identical logits."""
+    tables = action_tokenizer.tables(stats, device=logits.device)
+    return ops.argmax_detokenize_unnormalize(logits, int(action_tokenizer.tokenizer.vocab_size), tables)

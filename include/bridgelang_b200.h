@@ -102,6 +102,14 @@ long long blb_launch_count(void);
 /* 0 = auto, 1 = cta_group::1 tiles (128xBN), 2 = cta_group::2 CTA pairs (256xBN) */
 void blb_set_gemm_cta_group(int ctas);
 
+/* Per-launch device timing for the roofline report (off by default).  When enabled every kernel launch is
+ * bracketed by CUDA events on its stream; after the caller has synchronised, blb_timing_collect sums the elapsed
+ * milliseconds, the algorithmic work (FLOPs for categories 0/1, bytes for 2/3) and the launch count of one
+ * category: 0 = tcgen05 GEMM, 1 = attention, 2 = LayerNorm, 3 = other.  blb_timing_reset drops the records. */
+void blb_timing_enable(int on);
+void blb_timing_reset(void);
+int blb_timing_collect(int category, double* ms, double* work, long long* launches);
+
 /* ---- primitive operators (each replaces one library call of the reference; used by the parity tests) --- */
 /* C = A[M,K] (bf16, pitch lda) x W[N,K]^T (bf16, pitch ldw) with a fused epilogue.
  * Replaces nn.Linear (+GELU / +LayerScale+residual) reached via timm Attention/Mlp and nn_utils.py:42-48. */

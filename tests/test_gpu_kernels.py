@@ -1,0 +1,158 @@
+"""Per-kernel parity on a B200, through the C ABI: each kernel against an fp32 PyTorch evaluation of the same
+operator on the same bf16-rounded inputs, at tolerances tight enough to pin GELU flavour, LayerNorm eps, softmax
+scale and weight ordering (the 2e-2 end-to-end gate cannot see those)."""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from bridgelang_b200 import ops as _ops
+    return _ops
+
+
+def _gen(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+BF16_EPS = 2.0 ** -8
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("M,N,K", [
+    (128, 128, 64), (256, 256, 128), (261, 384, 1024), (1000, 768, 592), (522, 3072, 1024),
+    (512, 3456, 1152), (700, 4352, 1152), (515, 1152, 4352), (300, 8704, 2176), (130, 4096, 8704),
+])
+def test_gemm_bias(ops, ctas, M, N, K):
+    ops.set_gemm_cta_group(ctas)
+    g = _gen(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    out = ops.gemm(a, w, ops.EPI_BIAS, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    assert _rel(out, ref) < 1.5 * BF16_EPS
+    ops.set_gemm_cta_group(0)
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+def test_gemm_gelu_is_exact_erf(ops, ctas):
+    """acc[m,n] = W[n, m % K] exactly (A is a 0/1 selector), so the epilogue's activation is isolated; inputs sit
+    in [-3,-1.5] where erf- and tanh-GELU differ by ~1e-4 systematically (bf16 rounding noise averages out)."""
+    ops.set_gemm_cta_group(ctas)
+    M, N, K = 256, 256, 64
+    g = _gen(5)
+    w = (-(torch.rand(N, K, device="cuda", generator=g) * 1.5 + 1.5)).bfloat16()
+    a = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    a[torch.arange(M), torch.arange(M) % K] = 1
+    bias = torch.zeros(N, device="cuda")
+    out = ops.gemm(a, w, ops.EPI_BIAS_GELU, bias=bias).float()
+    x = w.float().t()[torch.arange(M) % K]                     # [M, N]
+    ref_erf, ref_tanh = F.gelu(x), F.gelu(x, approximate="tanh")
+    assert (out - ref_erf).abs().max() < 5e-4                # |gelu| <= 0.11 here: half a bf16 ulp is 2.4e-4
+    assert abs((out - ref_erf).mean().item()) < 1e-5
+    assert abs((out - ref_tanh).mean().item()) > 4e-5
+    ops.set_gemm_cta_group(0)
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("with_gamma", [True, False])
+def test_gemm_residual_layerscale_and_concat_write(ops, ctas, with_gamma):
+    ops.set_gemm_cta_group(ctas)
+    B, T, prefix, N, K = 3, 261, 5, 1024, 512
+    M = B * T
+    g = _gen(9)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5 if with_gamma else None
+    resid0 = torch.randn(M, N, device="cuda", generator=g)
+    resid = resid0.clone()
+    concat = torch.full((B * 256, 2176), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, ops.EPI_RESIDUAL, bias=bias, gamma=gamma, resid=resid, out=concat, out_col_off=1024,
+             tok_in=T, tok_out=256, tok_shift=-prefix)
+    branch = a.float() @ w.float().t() + bias
+    ref = resid0 + (gamma * branch if with_gamma else branch)
+    assert _rel(resid, ref) < 2e-5                              # fp32 residual stream: no bf16 rounding anywhere
+    want = ref.view(B, T, N)[:, prefix:].reshape(B * 256, N)
+    assert _rel(concat[:, 1024:1024 + N], want) < BF16_EPS
+    assert bool((concat[:, :1024] == 7.0).all()) and bool((concat[:, 1024 + N:] == 7.0).all())
+    ops.set_gemm_cta_group(0)
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+def test_gemm_patch_epilogue_row_remap_and_pos(ops, ctas):
+    ops.set_gemm_cta_group(ctas)
+    B, T, prefix, N, K = 2, 261, 5, 1024, 592
+    g = _gen(3)
+    a = (torch.randn(B * 256, K, device="cuda", generator=g)).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    pos = torch.randn(256, N, device="cuda", generator=g)
+    resid = torch.full((B * T, N), -3.0, device="cuda")
+    ops.gemm(a, w, ops.EPI_PATCH, bias=bias, resid=resid, pos=pos, tok_in=256, tok_out=T, tok_shift=prefix)
+    ref = (a.float() @ w.float().t() + bias).view(B, 256, N) + pos
+    got = resid.view(B, T, N)
+    assert _rel(got[:, prefix:], ref) < 2e-5
+    assert bool((got[:, :prefix] == -3.0).all())
+    ops.set_gemm_cta_group(0)
+
+
+def test_gemm_rejects_unsupported_shapes(ops):
+    a = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(100, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="status -2"):
+        ops.gemm(a, w, ops.EPI_BIAS, bias=None)
+
+
+@pytest.mark.parametrize("D", [1024, 1152])
+def test_layernorm(ops, D):
+    g = _gen(D)
+    x = torch.randn(1000, D, device="cuda", generator=g) * 3 + 1
+    x[7] = 1.0 + 1e-3 * torch.randn(D, device="cuda", generator=g)   # var ~1e-6: eps = 1e-6 matters here
+    w = torch.rand(D, device="cuda", generator=g) + 0.5
+    b = torch.randn(D, device="cuda", generator=g) * 0.1
+    y = ops.layernorm(x, w, b, 1e-6).float()
+    ref = F.layer_norm(x, (D,), w, b, 1e-6)
+    assert torch.allclose(y, ref, rtol=2 * BF16_EPS, atol=2e-3)
+    wrong_eps = F.layer_norm(x[7:8], (D,), w, b, 1e-5)
+    assert (y[7:8] - ref[7:8]).abs().max() < 0.1 * (wrong_eps - ref[7:8]).abs().max()
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(3, 261, 16, 64), (3, 256, 16, 72), (2, 64, 2, 64), (1, 7, 1, 72)])
+def test_attention(ops, B, T, H, hd):
+    g = _gen(T + hd)
+    D = H * hd
+    qkv = torch.randn(B * T, 3 * D, device="cuda", generator=g).bfloat16()
+    out = ops.attention(qkv, B, T, H, hd)
+    q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, D)
+    assert _rel(out, ref) < 6e-3
+    wrong = F.scaled_dot_product_attention(q, k, v, scale=1.0 / 8.5).transpose(1, 2).reshape(B * T, D)
+    assert _rel(out, ref) < 0.2 * _rel(wrong, ref)
+
+
+def test_im2col_matches_unfold_and_conv_weight_order(ops):
+    g = _gen(1)
+    px = torch.randn(3, 3, 224, 224, device="cuda", generator=g).bfloat16()
+    cols = ops.im2col_patch14(px)
+    ref = F.unfold(px.float(), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(cols[:, :588].float(), ref)
+    assert bool((cols[:, 588:] == 0).all())
+    # as a GEMM it equals Conv2d with the weight flattened in (c, kh, kw) order
+    w = (torch.randn(128, 3, 14, 14, device="cuda", generator=g) * 0.05).bfloat16()
+    wp = torch.zeros(128, 592, device="cuda", dtype=torch.bfloat16)
+    wp[:, :588] = w.reshape(128, 588)
+    bias = torch.zeros(128, device="cuda")
+    out = ops.gemm(cols, wp, ops.EPI_BIAS, bias=bias)
+    conv = F.conv2d(px.float(), w.float(), stride=14).flatten(2).transpose(1, 2).reshape(-1, 128)
+    assert _rel(out, conv) < 1.5 * BF16_EPS

@@ -10,6 +10,8 @@
 //
 // v1 numerics/structure: one CTA per (image, head), 4 warps x 16 query rows per pass, online softmax over
 // 64-key blocks, bf16 mma.sync m16n8k16 with fp32 accumulation.
+#include <cstdlib>
+
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -40,7 +42,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 template <int HD, int HDP>
 __global__ void __launch_bounds__(128, 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H,
-                 float scale_log2) {
+                 float scale_log2, int q_begin) {
   constexpr int PITCH = HDP + 8;        // +16 B per row keeps ldmatrix conflict-free
   constexpr int KSTEPS = HDP / 16;
   constexpr int NT_O = HDP / 8;
@@ -77,7 +79,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const int n_kblocks = TKP / 64;
   const int g = lane >> 2, t4 = lane & 3;
 
-  for (int q0 = 0; q0 < T; q0 += 64) {
+  for (int q0 = q_begin; q0 < T; q0 += 64) {
     __syncthreads();   // previous pass finished reading sQ
     for (int i = threadIdx.x; i < 64 * CHUNKS; i += blockDim.x) {
       const int r = i / CHUNKS, c = i - r * CHUNKS;
@@ -195,7 +197,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 }
 
 template <int HD, int HDP>
-static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream) {
+static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int q_begin,
+                            cudaStream_t stream) {
   constexpr int PITCH = HDP + 8;
   const int TKP = (T + 63) & ~63;
   const int smem = (2 * TKP + 64) * PITCH * 2;
@@ -208,17 +211,30 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
     configured_smem = smem;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T) * T * HD, stream);
-  kern<<<B * H, 128, smem, stream>>>(qkv, out, T, H, scale_log2);
+  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T - q_begin) * T * HD, stream);
+  kern<<<B * H, 128, smem, stream>>>(qkv, out, T, H, scale_log2, q_begin);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
 }
 
+int attention_tc_first256(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd,
+                          cudaStream_t stream);   // attention_tc.cu
+
+static bool g_attn_v1_only = getenv("BLB_ATTN_V1") != nullptr;   // A/B switch: mma.sync kernel for everything
+
 int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream) {
   if (qkv == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0) return BLB_ERR_ARG;
-  if (hd == 64) return launch_attention<64, 64>(qkv, out, B, T, H, stream);
-  if (hd == 72) return launch_attention<72, 80>(qkv, out, B, T, H, stream);
-  return BLB_ERR_SHAPE;
+  if (hd != 64 && hd != 72) return BLB_ERR_SHAPE;
+  int q_begin = 0;
+  if (!g_attn_v1_only) {
+    // tower shapes: the tcgen05 kernel takes query rows [0,256); DINOv2's 5 remaining rows go to the mma.sync kernel
+    const int rc = attention_tc_first256(qkv, out, B, T, H, hd, stream);
+    if (rc == 0) q_begin = 256;
+    else if (rc != BLB_ERR_SHAPE) return rc;
+  }
+  if (q_begin >= T) return 0;
+  if (hd == 64) return launch_attention<64, 64>(qkv, out, B, T, H, q_begin, stream);
+  return launch_attention<72, 80>(qkv, out, B, T, H, q_begin, stream);
 }
 
 }  // namespace blb

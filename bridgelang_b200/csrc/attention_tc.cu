@@ -1,0 +1,494 @@
+// attention_tc.cu — tcgen05/TMEM softmax attention for the two towers (the v2 path of attention.cu).
+//
+// timm Attention core: softmax(q·kᵀ·hd^-0.5)·v, no mask, 16 heads,
+//   DINOv2-reg4  T = 261 tokens, head_dim 64   →  template <64, 16>  (256 keys + 16-key tail block, 5 of them real)
+//   SigLIP       T = 256 tokens, head_dim 72   →  template <72, 0>   (d split 64 + 16; the 16-wide block is 32B-swizzled)
+// One persistent CTA per SM walks (image, head) units; per unit it handles the first 256 query rows as two
+// 128-row tiles (the T-256 remaining query rows of DINOv2 go to the mma.sync kernel in attention.cu).
+//
+//   warp 0    TMA producer: Q tiles, K, V straight out of the packed QKV GEMM output through a 4-D tensor map
+//             {d, 3·H head slots, token, image}; rows >= T and d >= head_dim are zero-filled by TMA (OOB)
+//   warp 1    MMA issuer:   S = Q·Kᵀ  (M128 × N256[+16], fp32 in TMEM columns [0,272))
+//                           O = P·V   (A = P from shared memory, B = V as an MN-major operand, TMEM [320,..))
+//   warp 2    TMEM allocator
+//   warps 4-11 softmax + epilogue: two groups of 4 warps split the S columns; a thread owns query row = TMEM lane:
+//             row max, exp2, row sum in fp32 (partials combined through smem), P rounded to bf16 into 128B-swizzled
+//             shared memory (the UMMA A-operand layout), then O / rowsum → bf16 → global
+// Issue order per tile g:  S(g) → [softmax(g) on the SIMT side ‖ PV(g-1) on the tensor pipe] → S(g+1) …
+// so the tensor pipe only ever exposes one Q·Kᵀ (~550 cycles) per ~2300-cycle MUFU-bound softmax.
+#include <algorithm>
+#include <cmath>
+
+#include "gemm.h"
+#include "ptx.cuh"
+
+namespace blb {
+
+namespace {
+
+constexpr int QT = 128;        // query rows per tile (UMMA M)
+constexpr int KMAIN = 256;     // keys in the main block (UMMA N of S)
+constexpr int TC_THREADS = 384;   // 4 control warps + 8 softmax/epilogue warps
+
+// ---- descriptors ------------------------------------------------------------------------------------
+// layout_type: 2 = SWIZZLE_128B, 6 = SWIZZLE_32B.  K-major operands: SBO = 8 rows * row_bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> f32; A K-major; B K-major (b_mn = 0) or MN-major (b_mn = 1)
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int HD, int KX>
+struct AttnCfg {
+  static constexpr bool SPLIT_D = HD > 64;                       // head_dim 72: d = 64 (SW128) + 16 (SW32, 8 real)
+  static constexpr int HDP = SPLIT_D ? 80 : 64;                  // O columns
+  static constexpr int Q_MAIN = QT * 128;                        // 16 KB
+  static constexpr int Q_X = SPLIT_D ? QT * 32 : 0;              // 4 KB
+  static constexpr int Q_BYTES = Q_MAIN + Q_X;
+  static constexpr int KV_MAIN = KMAIN * 128;                    // 32 KB
+  static constexpr int KV_TAIL = KX * 128;                       // 2 KB (16 keys)
+  static constexpr int KV_X = SPLIT_D ? KMAIN * 32 : 0;          // 8 KB
+  static constexpr int KV_BYTES = KV_MAIN + KV_TAIL + KV_X;
+  static constexpr int P_MAIN = 4 * QT * 128;                    // 4 blocks of 64 keys, 64 KB
+  static constexpr int P_TAIL = KX > 0 ? QT * 32 : 0;            // [128 x 16 keys] SW32, 4 KB
+  static constexpr int P_BYTES = P_MAIN + P_TAIL;
+  static constexpr int OFF_Q0 = 0;
+  static constexpr int OFF_Q1 = OFF_Q0 + Q_BYTES;
+  static constexpr int OFF_K = OFF_Q1 + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_XCHG = OFF_P + P_BYTES;               // row max [2][128] + row sums [2][2][128] (fp32)
+  static constexpr int OFF_BAR = OFF_XCHG + 6 * QT * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int S_COLS = KMAIN + KX;
+  static constexpr int O_COL0 = 320, O_COL1 = 416;
+  static_assert(Q_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0 && KV_MAIN % 1024 == 0, "1 KB aligned blocks");
+  static_assert(O_COL1 + HDP <= 512 && S_COLS <= O_COL0, "TMEM budget");
+};
+
+struct AttnMaps {
+  CUtensorMap q_main, kv_main, kv_tail, q_x, kv_x;
+};
+
+template <int HD, int KX>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out, int B, int T, int H,
+                    float scale_log2) {
+  using Cfg = AttnCfg<HD, KX>;
+  extern __shared__ uint8_t smem_raw_attn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_empty = bars + 5;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 7;
+  uint64_t* s_full = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* o_full = bars + 11;    // [2]
+  uint64_t* o_empty = bars + 13;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = B * H;
+  const int my_units = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int G = 2 * my_units;      // tiles this CTA processes
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q_main);
+    tma_prefetch_desc(&maps.kv_main);
+    if (KX > 0) tma_prefetch_desc(&maps.kv_tail);
+    if (Cfg::SPLIT_D) { tma_prefetch_desc(&maps.q_x); tma_prefetch_desc(&maps.kv_x); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  uint8_t* sQ[2] = {smem + Cfg::OFF_Q0, smem + Cfg::OFF_Q1};
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;
+
+  if (warp == 0) {
+    // ============================== TMA producer ===================================================
+    if (lane == 0) {
+      for (int i = 0; i < my_units; ++i) {
+        const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        const int b = u / H, h = u - b * H;
+        const uint32_t ph = static_cast<uint32_t>(i & 1);
+        mbar_wait(k_empty, ph ^ 1u);
+        mbar_expect_tx(k_full, Cfg::KV_BYTES);
+        tma_load_4d(sK, &maps.kv_main, k_full, 0, H + h, 0, b);
+        if (KX > 0) tma_load_4d(sK + Cfg::KV_MAIN, &maps.kv_tail, k_full, 0, H + h, KMAIN, b);
+        if (Cfg::SPLIT_D) tma_load_4d(sK + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, k_full, 64, H + h, 0, b);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_empty[t], ph ^ 1u);
+          mbar_expect_tx(&q_full[t], Cfg::Q_BYTES);
+          tma_load_4d(sQ[t], &maps.q_main, &q_full[t], 0, h, t * QT, b);
+          if (Cfg::SPLIT_D) tma_load_4d(sQ[t] + Cfg::Q_MAIN, &maps.q_x, &q_full[t], 64, h, t * QT, b);
+        }
+        mbar_wait(v_empty, ph ^ 1u);
+        mbar_expect_tx(v_full, Cfg::KV_BYTES);
+        tma_load_4d(sV, &maps.kv_main, v_full, 0, 2 * H + h, 0, b);
+        if (KX > 0) tma_load_4d(sV + Cfg::KV_MAIN, &maps.kv_tail, v_full, 0, 2 * H + h, KMAIN, b);
+        if (Cfg::SPLIT_D) tma_load_4d(sV + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, v_full, 64, 2 * H + h, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ====================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s_main = idesc_bf16(QT, KMAIN, 0);
+      constexpr uint32_t idesc_s_tail = idesc_bf16(QT, 16, 0);
+      constexpr uint32_t idesc_o_main = idesc_bf16(QT, 64, 1);
+      constexpr uint32_t idesc_o_x = idesc_bf16(QT, 16, 1);
+      for (int g = 0; g <= G; ++g) {
+        if (g > 0) {   // softmax(g-1) has read S and written P(g-1)
+          mbar_wait(p_full, static_cast<uint32_t>((g - 1) & 1));
+          tc_fence_after();
+        }
+        if (g < G) {
+          // ---------------- S(g) = Q · Kᵀ ----------------
+          const int t = g & 1, i = g >> 1;
+          const uint32_t ph = static_cast<uint32_t>(i & 1);
+          if (t == 0) mbar_wait(k_full, ph);
+          mbar_wait(&q_full[t], ph);
+          tc_fence_after();
+          const uint32_t qa = smem_u32(sQ[t]), ka = smem_u32(sK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16<1>(tmem_base, make_desc(qa, 1024, 2) + 2 * k, make_desc(ka, 1024, 2) + 2 * k, idesc_s_main,
+                         k > 0 ? 1u : 0u);
+          if (Cfg::SPLIT_D)
+            umma_bf16<1>(tmem_base, make_desc(qa + Cfg::Q_MAIN, 256, 6),
+                         make_desc(ka + Cfg::KV_MAIN + Cfg::KV_TAIL, 256, 6), idesc_s_main, 1u);
+          if (KX > 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16<1>(tmem_base + KMAIN, make_desc(qa, 1024, 2) + 2 * k,
+                           make_desc(ka + Cfg::KV_MAIN, 1024, 2) + 2 * k, idesc_s_tail, k > 0 ? 1u : 0u);
+          }
+          umma_commit<1>(s_full);
+          umma_commit<1>(&q_empty[t]);
+          if (t == 1) umma_commit<1>(k_empty);
+        }
+        if (g > 0) {
+          // ---------------- O(g-1) = P(g-1) · V ----------------
+          const int gp = g - 1, t = gp & 1, i = gp >> 1;
+          const uint32_t ph = static_cast<uint32_t>(i & 1);
+          if (t == 0) mbar_wait(v_full, ph);
+          mbar_wait(&o_empty[t], ph ^ 1u);
+          tc_fence_after();
+          const uint32_t o_col = tmem_base + static_cast<uint32_t>(t == 0 ? Cfg::O_COL0 : Cfg::O_COL1);
+          const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {   // 16 keys per step; P block j/4 (K-major SW128), V rows 16j.. (MN-major)
+            const uint64_t a = make_desc(pa + (j >> 2) * (QT * 128), 1024, 2) + 2 * (j & 3);
+            umma_bf16<1>(o_col, a, make_desc(va + j * 2048, 1024, 2), idesc_o_main, j > 0 ? 1u : 0u);
+            if (Cfg::SPLIT_D)
+              umma_bf16<1>(o_col + 64, a, make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6), idesc_o_x,
+                           j > 0 ? 1u : 0u);
+          }
+          if (KX > 0)
+            umma_bf16<1>(o_col, make_desc(pa + Cfg::P_MAIN, 256, 6), make_desc(va + Cfg::KV_MAIN, 1024, 2),
+                         idesc_o_main, 1u);
+          umma_commit<1>(p_empty);
+          umma_commit<1>(&o_full[t]);
+          if (t == 1) umma_commit<1>(v_empty);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ softmax + epilogue ===============================================
+    // 8 warps: warp-group wg = 0/1 owns S columns [0,128) / [128, 256+KX); both groups see all 128 rows
+    // (warps w and w+4 share TMEM lane quarter w%4), so every SM sub-partition runs two softmax warps whose
+    // TMEM-load / MUFU / shared-store latencies overlap.  Row max and row sum are combined through shared memory.
+    const int q = warp & 3;
+    const int wg = (warp - 4) >> 2;
+    const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int D = H * HD;
+    const int sw128 = (row & 7) << 4;                    // 16-byte chunk XOR of a 128B-swizzled row
+    const int sw32 = ((row >> 2) & 1) << 4;
+    float* xmax = reinterpret_cast<float*>(smem + Cfg::OFF_XCHG);            // [2 groups][128 rows]
+    float* xsum = xmax + 2 * QT;                                             // [2 tile parities][2 groups][128]
+    float sum_prev = 0.f;
+    const int col_base = wg * 128;
+
+    auto epilogue = [&](int gp, float own_sum) {
+      const int t = gp & 1, i = gp >> 1;
+      const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      const int b = u / H, h = u - b * H;
+      const float inv = 1.0f / (own_sum + xsum[(gp & 1) * 2 * QT + (wg ^ 1) * QT + row]);
+      mbar_wait(&o_full[t], static_cast<uint32_t>(i & 1));
+      tc_fence_after();
+      const uint32_t o_addr = lane_addr + static_cast<uint32_t>(t == 0 ? Cfg::O_COL0 : Cfg::O_COL1);
+      __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + t * QT + row) * D + h * HD;
+      uint32_t r[32];
+      uint32_t rx[16];
+      tmem_ld_32x32(o_addr + wg * 32, r);               // this group's 32 of the 64 main O columns
+      if (Cfg::SPLIT_D && wg == 1) tmem_ld_32x16(o_addr + 64, rx);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + wg * 32 + j) = pk;
+      }
+      if (Cfg::SPLIT_D && wg == 1) {
+        uint4 pk;
+        pk.x = pack_bf16x2(__uint_as_float(rx[0]) * inv, __uint_as_float(rx[1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(rx[2]) * inv, __uint_as_float(rx[3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(rx[4]) * inv, __uint_as_float(rx[5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(rx[6]) * inv, __uint_as_float(rx[7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 64) = pk;        // d 64..71 (72..79 are padding)
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[t]);
+    };
+
+    // exp2 + bf16 pack + swizzled store of one 32-column chunk; returns the chunk's partial row sum
+    auto exp_store = [&](const uint32_t (&r)[32], int c_global, float ms) -> float {
+      float s0 = 0.f, s1 = 0.f;
+      uint8_t* prow = sP + (c_global >> 1) * (QT * 128) + row * 128;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] = ex2_approx(fmaf(__uint_as_float(r[j + e]), scale_log2, -ms));
+        s0 += (p[0] + p[1]) + (p[2] + p[3]);
+        s1 += (p[4] + p[5]) + (p[6] + p[7]);
+        uint4 pk;
+        pk.x = pack_bf16x2(p[0], p[1]);
+        pk.y = pack_bf16x2(p[2], p[3]);
+        pk.z = pack_bf16x2(p[4], p[5]);
+        pk.w = pack_bf16x2(p[6], p[7]);
+        const int chunk = ((c_global & 1) * 4 + (j >> 3)) << 4;   // 16-byte chunk inside the 64-key block row
+        *reinterpret_cast<uint4*>(prow + (chunk ^ sw128)) = pk;
+      }
+      return s0 + s1;
+    };
+    auto max32 = [&](const uint32_t (&r)[32], float m) -> float {
+      float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        m0 = fmaxf(m0, __uint_as_float(r[j]));
+        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+        m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+        m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+      }
+      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    };
+
+    for (int g = 0; g < G; ++g) {
+      mbar_wait(s_full, static_cast<uint32_t>(g & 1));
+      tc_fence_after();
+      // ---- pass 1: partial row max over this group's columns (TMEM loads one chunk ahead) ----
+      float m = -INFINITY;
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(lane_addr + col_base, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(lane_addr + col_base + 32, rb);
+        m = max32(ra, m);
+        tmem_ld_wait();
+        tmem_ld_32x32(lane_addr + col_base + 64, ra);
+        m = max32(rb, m);
+        tmem_ld_wait();
+        tmem_ld_32x32(lane_addr + col_base + 96, rb);
+        m = max32(ra, m);
+        tmem_ld_wait();
+        m = max32(rb, m);
+      }
+      if (KX > 0 && wg == 1) {
+        uint32_t r[16];
+        tmem_ld_32x16(lane_addr + KMAIN, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (KMAIN + j < T) m = fmaxf(m, __uint_as_float(r[j]));
+      }
+      xmax[wg * QT + row] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");    // the two groups exchange their partial maxima
+      m = fmaxf(m, xmax[(wg ^ 1) * QT + row]);
+      const float ms = m * scale_log2;
+      // P(g-1) must have been consumed by PV(g-1) before it is overwritten
+      if (g > 0) mbar_wait(p_empty, static_cast<uint32_t>((g - 1) & 1));
+      // ---- pass 2: p = 2^(s*c - m*c), partial row sum, bf16 P into the swizzled A-operand layout ----
+      float sum = 0.f;
+      {
+        uint32_t ra[32], rb[32];
+        const int c0 = wg * 4;
+        tmem_ld_32x32(lane_addr + col_base, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(lane_addr + col_base + 32, rb);
+        sum += exp_store(ra, c0, ms);
+        tmem_ld_wait();
+        tmem_ld_32x32(lane_addr + col_base + 64, ra);
+        sum += exp_store(rb, c0 + 1, ms);
+        tmem_ld_wait();
+        tmem_ld_32x32(lane_addr + col_base + 96, rb);
+        sum += exp_store(ra, c0 + 2, ms);
+        tmem_ld_wait();
+        sum += exp_store(rb, c0 + 3, ms);
+      }
+      if (KX > 0 && wg == 1) {
+        uint32_t r[16];
+        tmem_ld_32x16(lane_addr + KMAIN, r);
+        tmem_ld_wait();
+        uint8_t* prow = sP + Cfg::P_MAIN + row * 32;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            p[e] = (KMAIN + j + e < T) ? ex2_approx(fmaf(__uint_as_float(r[j + e]), scale_log2, -ms)) : 0.f;
+            sum += p[e];
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(p[0], p[1]);
+          pk.y = pack_bf16x2(p[2], p[3]);
+          pk.z = pack_bf16x2(p[4], p[5]);
+          pk.w = pack_bf16x2(p[6], p[7]);
+          *reinterpret_cast<uint4*>(prow + (((j >> 3) << 4) ^ sw32)) = pk;
+        }
+      }
+      xsum[(g & 1) * 2 * QT + wg * QT + row] = sum;   // read by the other group in this tile's epilogue
+      fence_proxy_async_smem();     // make the generic-proxy P stores visible to the tensor core (async proxy)
+      tc_fence_before();            // and order our TMEM reads of S before the next S MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- epilogue of the previous tile (its PV was issued right after P(g-1) became ready; the other group's
+      //      partial sum of tile g-1 was published before this tile's bar.sync) ----
+      if (g > 0) epilogue(g - 1, sum_prev);
+      sum_prev = sum;
+    }
+    if (G > 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");    // partial sums of the last tile are visible
+      epilogue(G - 1, sum_prev);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D view of the packed qkv tensor: {d (hd), head slot (3H), token (T), image (B)}
+int make_qkv_map(CUtensorMap* map, const void* qkv, int B, int T, int H, int hd, int box_d, int box_rows,
+                 CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return BLB_ERR_DRIVER;
+  const uint64_t D3 = static_cast<uint64_t>(3) * H * hd;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(hd), static_cast<cuuint64_t>(3 * H), static_cast<cuuint64_t>(T),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(hd) * 2, D3 * 2, D3 * 2 * static_cast<cuuint64_t>(T)};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), 1, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(qkv), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : BLB_ERR_DRIVER;
+}
+
+template <int HD, int KX>
+int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD, KX>;
+  AttnMaps maps;
+  int rc = make_qkv_map(&maps.q_main, qkv, B, T, H, HD, 64, QT, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == 0) rc = make_qkv_map(&maps.kv_main, qkv, B, T, H, HD, 64, KMAIN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == 0) rc = make_qkv_map(&maps.kv_tail, qkv, B, T, H, HD, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc == 0) rc = make_qkv_map(&maps.q_x, qkv, B, T, H, HD, 16, QT, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc == 0) rc = make_qkv_map(&maps.kv_x, qkv, B, T, H, HD, 16, KMAIN, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc != 0) return rc;
+  auto kern = attention_tc_kernel<HD, KX>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int grid = std::min(num_sms(), B * H);
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * 256.0 * T * HD, stream);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, out, B, T, H, scale_log2);
+  count_launch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+// Handles query rows [0, 256) of every (image, head); returns BLB_ERR_SHAPE when (T, hd) is not one of the two
+// tower configurations this kernel is built for (the caller then uses the mma.sync kernel for everything).
+int attention_tc_first256(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd,
+                          cudaStream_t stream) {
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return BLB_ERR_ALIGN;
+  if (hd == 64 && T == 256) return launch_tc<64, 0>(qkv, out, B, T, H, stream);
+  if (hd == 64 && T > 256 && T <= 272) return launch_tc<64, 16>(qkv, out, B, T, H, stream);
+  if (hd == 72 && T == 256) return launch_tc<72, 0>(qkv, out, B, T, H, stream);
+  return BLB_ERR_SHAPE;
+}
+
+}  // namespace blb

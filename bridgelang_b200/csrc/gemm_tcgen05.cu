@@ -14,6 +14,7 @@
 //   warp 3      idle
 //   warps 4-11  epilogue       (tcgen05.ld → registers → fused bias/GELU/LayerScale/residual → global)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstdlib>
 #include <vector>
 
 #include "gemm.h"
@@ -27,16 +28,20 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
 
-template <int BN, int CTAS>
+constexpr int RCHUNK_BYTES = 32 * 32 * 4;   // one epilogue warp's [32 rows x 32 cols] fp32 residual chunk
+
+template <int BN, int CTAS, bool RTMA = false>
 struct GemmCfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of W this CTA stages per k-block
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+  // RTMA: every epilogue warp owns two TMA-fed residual chunk buffers (prefetched two chunks ahead)
+  static constexpr int EPI_BYTES = RTMA ? NUM_EPI_WARPS * 2 * RCHUNK_BYTES : 0;
+  static constexpr int STAGES = (200 * 1024 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 512;                    // 2 accumulator stages of BN (<=256) columns
   static constexpr int ACC_STRIDE = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ bool map_row(const GemmEpilogue& e, int row, int& dst_row, int& tok) {
@@ -52,23 +57,26 @@ __device__ __forceinline__ bool map_row(const GemmEpilogue& e, int row, int& dst
   return t2 >= 0 && t2 < e.tok_out;
 }
 
-template <int BN, int CTAS, int MODE>
+template <int BN, int CTAS, int MODE, bool RTMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-                 int K, GemmEpilogue epi) {
-  using Cfg = GemmCfg<BN, CTAS>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K, GemmEpilogue epi) {
+  using Cfg = GemmCfg<BN, CTAS, RTMA>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(!RTMA || MODE == EPI_RESIDUAL, "TMA-staged residual only exists for EPI_RESIDUAL");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_r = smem + STAGES * Cfg::STAGE_BYTES;                 // [8 warps][2][4 KB] residual chunks (RTMA)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]   TMA → MMA
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]   MMA → TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]        MMA → epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]        epilogue → MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* rld_bar = bars + 2 * STAGES + 4;      // [8][2]     residual chunk TMA → epilogue warp (RTMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,6 +94,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (RTMA) tma_prefetch_desc(&tmap_r);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -96,6 +105,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], CTAS * NUM_EPI_WARPS);
     }
+    if (RTMA)
+      for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(&rld_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -180,6 +191,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     static_assert(COLS_PER_WARP % 32 == 0, "BN/2 must be a multiple of 32");
     int acc = 0;
     uint32_t acc_phase = 0;
+    // RTMA: flat sequence seq = local_tile * CHUNKS + chunk; residual chunk `seq` lands in buffer seq & 1 of this
+    // warp, its TMA is issued two sequence steps ahead (i.e. possibly already for the next tile).
+    uint8_t* rbuf = smem_r + ew * 2 * RCHUNK_BYTES;
+    uint64_t* rbar = rld_bar + ew * 2;
+    auto issue_resid = [&](int sq) {
+      const int lt = sq / CHUNKS, c = sq - lt * CHUNKS;
+      const int tl = first_tile + lt * tile_step;
+      if (tl >= num_tiles) return;
+      const int mb = tl / n_tiles, nb = tl - mb * n_tiles;
+      const int r0 = mb * tile_m + static_cast<int>(cta_rank) * BM + quarter * 32;
+      const int c0 = nb * BN + half * COLS_PER_WARP + c * 32;
+      mbar_expect_tx(&rbar[sq & 1], RCHUNK_BYTES);
+      tma_load_2d(rbuf + (sq & 1) * RCHUNK_BYTES, &tmap_r, &rbar[sq & 1], c0, r0);
+    };
+    int seq = 0;
+    if (RTMA && lane == 0) {
+      issue_resid(0);
+      issue_resid(1);
+    }
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
@@ -199,6 +229,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                           static_cast<uint32_t>(acc * Cfg::ACC_STRIDE + col_in_tile),
                       r);
+        float xres[RTMA ? 32 : 1];
+        if constexpr (RTMA) {
+          // this lane's row of the TMA-staged residual chunk (128-byte rows, 128B-swizzled → conflict-free)
+          mbar_wait(&rbar[seq & 1], static_cast<uint32_t>((seq >> 1) & 1));
+          const uint8_t* src = rbuf + (seq & 1) * RCHUNK_BYTES + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x4 = *reinterpret_cast<const float4*>(src + ((j ^ (lane & 7)) << 4));
+            xres[4 * j] = x4.x; xres[4 * j + 1] = x4.y; xres[4 * j + 2] = x4.z; xres[4 * j + 3] = x4.w;
+          }
+          // WAR across proxies: the refill below is an async-proxy (TMA) write to the buffer just read through
+          // the generic proxy.  Make sure the loads have landed (consume the registers), order them against
+          // the async proxy, and only then let lane 0 issue the TMA for the chunk two steps ahead.
+#pragma unroll
+          for (int j = 0; j < 32; ++j) asm volatile("" : "+f"(xres[j]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) issue_resid(seq + 2);
+          ++seq;
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -251,7 +301,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              float4 x4 = *reinterpret_cast<const float4*>(x + j);
+              float4 x4;
+              if constexpr (RTMA) x4 = make_float4(xres[j], xres[j + 1], xres[j + 2], xres[j + 3]);
+              else x4 = *reinterpret_cast<const float4*>(x + j);
               x4.x += v[j]; x4.y += v[j + 1]; x4.z += v[j + 2]; x4.w += v[j + 3];
               v[j] = x4.x; v[j + 1] = x4.y; v[j + 2] = x4.z; v[j + 3] = x4.w;
               *reinterpret_cast<float4*>(x + j) = x4;
@@ -313,23 +365,30 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 [rows, cols] row-major (pitch ld elements) → TMA map with a {64, box_rows} box, 128B swizzle.
-int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// row-major [rows, cols] matrix (pitch ld elements of elem_bytes) → 2-D TMA map with a {box_cols, box_rows} box.
+static int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* ptr, uint64_t rows,
+                        uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return BLB_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return BLB_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0) return BLB_ERR_ALIGN;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint64_t strides[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : BLB_ERR_DRIVER;
+}
+
+// bf16 [rows, cols] row-major (pitch ld elements) → TMA map with a {64, box_rows} box, 128B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, rows, cols, ld, static_cast<uint32_t>(BK),
+                      box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 static int g_num_sms = 0;
 static int g_force_ctas = 0;   // 0 = auto, 1 / 2 = forced (tests and A/B measurements)
+static bool g_resid_direct = getenv("BLB_RESID_DIRECT") != nullptr;   // A/B switch: residual via plain loads
 static long long g_launches = 0;
 
 void gemm_set_cta_group(int ctas) { g_force_ctas = ctas; }
@@ -385,11 +444,11 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int CTAS, int MODE>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpilogue& epi,
-                  cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTAS>;
-  auto kern = gemm_bf16_kernel<BN, CTAS, MODE>;
+template <int BN, int CTAS, int MODE, bool RTMA>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, int M, int N, int K,
+                  const GemmEpilogue& epi, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CTAS, RTMA>;
+  auto kern = gemm_bf16_kernel<BN, CTAS, MODE, RTMA>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -414,7 +473,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   TimingScope ts(TIME_GEMM, 2.0 * M * N * K, stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, epi);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, M, N, K, epi);
   count_launch(1);
   return static_cast<int>(e);
 }
@@ -423,10 +482,18 @@ template <int BN, int CTAS>
 static int launch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const GemmEpilogue& epi, cudaStream_t s) {
   switch (mode) {
-    case EPI_BIAS: return launch<BN, CTAS, EPI_BIAS>(ta, tb, M, N, K, epi, s);
-    case EPI_BIAS_GELU: return launch<BN, CTAS, EPI_BIAS_GELU>(ta, tb, M, N, K, epi, s);
-    case EPI_RESIDUAL: return launch<BN, CTAS, EPI_RESIDUAL>(ta, tb, M, N, K, epi, s);
-    case EPI_PATCH: return launch<BN, CTAS, EPI_PATCH>(ta, tb, M, N, K, epi, s);
+    case EPI_BIAS: return launch<BN, CTAS, EPI_BIAS, false>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_BIAS_GELU: return launch<BN, CTAS, EPI_BIAS_GELU, false>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_PATCH: return launch<BN, CTAS, EPI_PATCH, false>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_RESIDUAL: {
+      if (g_resid_direct) return launch<BN, CTAS, EPI_RESIDUAL, false>(ta, tb, ta, M, N, K, epi, s);
+      CUtensorMap tr;   // fp32 residual stream [M, N] → [32 x 32] boxes, 128B-swizzled rows
+      int rc = make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.resid, static_cast<uint64_t>(M),
+                            static_cast<uint64_t>(N), static_cast<uint64_t>(epi.ld_resid), 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != 0) return rc;
+      return launch<BN, CTAS, EPI_RESIDUAL, true>(ta, tb, tr, M, N, K, epi, s);
+    }
   }
   return BLB_ERR_ARG;
 }

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "blb_status_string": (C.c_char_p, [C.c_int]),
     "blb_launch_count": (C.c_longlong, []),
     "blb_set_gemm_cta_group": (None, [C.c_int]),
+    "blb_debug_attention_trace": (None, [C.c_void_p]),
     "blb_timing_enable": (None, [C.c_int]),
     "blb_timing_reset": (None, []),
     "blb_timing_collect": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -66,6 +66,33 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] · B[smem]: A = bf16 P, row i in TMEM lane i, two consecutive k per 32-bit column
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int HD, int KX>
 struct AttnCfg {
   static constexpr bool SPLIT_D = HD > 64;                       // head_dim 72: d = 64 (SW128) + 16 (SW32, 8 real)
@@ -77,21 +104,20 @@ struct AttnCfg {
   static constexpr int KV_TAIL = KX * 128;                       // 2 KB (16 keys)
   static constexpr int KV_X = SPLIT_D ? KMAIN * 32 : 0;          // 8 KB
   static constexpr int KV_BYTES = KV_MAIN + KV_TAIL + KV_X;
-  static constexpr int P_MAIN = 4 * QT * 128;                    // 4 blocks of 64 keys, 64 KB
-  static constexpr int P_TAIL = KX > 0 ? QT * 32 : 0;            // [128 x 16 keys] SW32, 4 KB
-  static constexpr int P_BYTES = P_MAIN + P_TAIL;
   static constexpr int OFF_Q0 = 0;
   static constexpr int OFF_Q1 = OFF_Q0 + Q_BYTES;
   static constexpr int OFF_K = OFF_Q1 + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_BYTES;
-  static constexpr int OFF_XCHG = OFF_P + P_BYTES;               // row max [2][128] + row sums [2][2][128] (fp32)
+  static constexpr int OFF_XCHG = OFF_V + KV_BYTES;              // row max [2][128] + row sums [2][2][128] (fp32)
   static constexpr int OFF_BAR = OFF_XCHG + 6 * QT * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  // TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [P_COL, P_COL + (256+KX)/2) | O fp32 [O_COL, O_COL + HDP)
   static constexpr int S_COLS = KMAIN + KX;
-  static constexpr int O_COL0 = 320, O_COL1 = 416;
+  static constexpr int P_COL = S_COLS;
+  static constexpr int P_COLS = S_COLS / 2;
+  static constexpr int O_COL = P_COL + P_COLS;
   static_assert(Q_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0 && KV_MAIN % 1024 == 0, "1 KB aligned blocks");
-  static_assert(O_COL1 + HDP <= 512 && S_COLS <= O_COL0, "TMEM budget");
+  static_assert(O_COL + HDP <= 512, "TMEM budget");
 };
 
 struct AttnMaps {
@@ -101,7 +127,15 @@ struct AttnMaps {
 template <int HD, int KX>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out, int B, int T, int H,
-                    float scale_log2) {
+                    float scale_log2, long long* trace) {
+  // trace (debug only, normally nullptr): CTA 0 records clock64() at pipeline events of tiles [8, 16):
+  // trace[(g-8)*16 + e]; e: 0 mma:p_full seen, 1 mma:S issued, 2 mma:PV waits done, 3 mma:PV issued,
+  //                         8 sm:s_full seen, 9 sm:pass1 done, 10 sm:bar done, 11 sm:p_empty seen, 12 sm:pass2 done,
+  //                         13 sm:epilogue o_full seen, 14 sm:epilogue done
+#define BLB_TRACE(g_, e_)                                                                   \
+  do {                                                                                      \
+    if (trace != nullptr && blockIdx.x == 0 && (g_) >= 8 && (g_) < 16) trace[((g_) - 8) * 16 + (e_)] = clock64(); \
+  } while (0)
   using Cfg = AttnCfg<HD, KX>;
   extern __shared__ uint8_t smem_raw_attn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
@@ -115,8 +149,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
   uint64_t* s_full = bars + 8;
   uint64_t* p_full = bars + 9;
   uint64_t* p_empty = bars + 10;
-  uint64_t* o_full = bars + 11;    // [2]
-  uint64_t* o_empty = bars + 13;   // [2]
+  uint64_t* o_full = bars + 11;
+  uint64_t* o_empty = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(p_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 8); }
+    mbar_init(o_full, 1); mbar_init(o_empty, 8);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
@@ -146,7 +180,6 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
   uint8_t* sQ[2] = {smem + Cfg::OFF_Q0, smem + Cfg::OFF_Q1};
   uint8_t* sK = smem + Cfg::OFF_K;
   uint8_t* sV = smem + Cfg::OFF_V;
-  uint8_t* sP = smem + Cfg::OFF_P;
 
   if (warp == 0) {
     // ============================== TMA producer ===================================================
@@ -184,6 +217,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         if (g > 0) {   // softmax(g-1) has read S and written P(g-1)
           mbar_wait(p_full, static_cast<uint32_t>((g - 1) & 1));
           tc_fence_after();
+          BLB_TRACE(g, 0);
         }
         if (g < G) {
           // ---------------- S(g) = Q · Kᵀ ----------------
@@ -207,31 +241,33 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
                            make_desc(ka + Cfg::KV_MAIN, 1024, 2) + 2 * k, idesc_s_tail, k > 0 ? 1u : 0u);
           }
           umma_commit<1>(s_full);
+          BLB_TRACE(g, 1);
           umma_commit<1>(&q_empty[t]);
           if (t == 1) umma_commit<1>(k_empty);
         }
         if (g > 0) {
-          // ---------------- O(g-1) = P(g-1) · V ----------------
+          // ---------------- O(g-1) = P(g-1) · V   (A = P in TMEM, B = V as an MN-major smem operand) ----------------
           const int gp = g - 1, t = gp & 1, i = gp >> 1;
           const uint32_t ph = static_cast<uint32_t>(i & 1);
           if (t == 0) mbar_wait(v_full, ph);
-          mbar_wait(&o_empty[t], ph ^ 1u);
+          mbar_wait(o_empty, static_cast<uint32_t>(gp & 1) ^ 1u);   // epilogue(g-2) drained the O accumulator
           tc_fence_after();
-          const uint32_t o_col = tmem_base + static_cast<uint32_t>(t == 0 ? Cfg::O_COL0 : Cfg::O_COL1);
-          const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+          BLB_TRACE(g, 2);
+          const uint32_t o_col = tmem_base + Cfg::O_COL;
+          const uint32_t p_col = tmem_base + Cfg::P_COL;
+          const uint32_t va = smem_u32(sV);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {   // 16 keys per step; P block j/4 (K-major SW128), V rows 16j.. (MN-major)
-            const uint64_t a = make_desc(pa + (j >> 2) * (QT * 128), 1024, 2) + 2 * (j & 3);
-            umma_bf16<1>(o_col, a, make_desc(va + j * 2048, 1024, 2), idesc_o_main, j > 0 ? 1u : 0u);
+          for (int j = 0; j < 16; ++j) {   // 16 keys per step: 8 packed P columns, V rows 16j..16j+15
+            umma_bf16_ts(o_col, p_col + j * 8, make_desc(va + j * 2048, 1024, 2), idesc_o_main, j > 0 ? 1u : 0u);
             if (Cfg::SPLIT_D)
-              umma_bf16<1>(o_col + 64, a, make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6), idesc_o_x,
-                           j > 0 ? 1u : 0u);
+              umma_bf16_ts(o_col + 64, p_col + j * 8, make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6),
+                           idesc_o_x, j > 0 ? 1u : 0u);
           }
           if (KX > 0)
-            umma_bf16<1>(o_col, make_desc(pa + Cfg::P_MAIN, 256, 6), make_desc(va + Cfg::KV_MAIN, 1024, 2),
-                         idesc_o_main, 1u);
+            umma_bf16_ts(o_col, p_col + 128, make_desc(va + Cfg::KV_MAIN, 1024, 2), idesc_o_main, 1u);
           umma_commit<1>(p_empty);
-          umma_commit<1>(&o_full[t]);
+          BLB_TRACE(g, 3);
+          umma_commit<1>(o_full);
           if (t == 1) umma_commit<1>(v_empty);
         }
       }
@@ -246,8 +282,6 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int D = H * HD;
-    const int sw128 = (row & 7) << 4;                    // 16-byte chunk XOR of a 128B-swizzled row
-    const int sw32 = ((row >> 2) & 1) << 4;
     float* xmax = reinterpret_cast<float*>(smem + Cfg::OFF_XCHG);            // [2 groups][128 rows]
     float* xsum = xmax + 2 * QT;                                             // [2 tile parities][2 groups][128]
     float sum_prev = 0.f;
@@ -258,9 +292,10 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       const int b = u / H, h = u - b * H;
       const float inv = 1.0f / (own_sum + xsum[(gp & 1) * 2 * QT + (wg ^ 1) * QT + row]);
-      mbar_wait(&o_full[t], static_cast<uint32_t>(i & 1));
+      mbar_wait(o_full, static_cast<uint32_t>(gp & 1));
       tc_fence_after();
-      const uint32_t o_addr = lane_addr + static_cast<uint32_t>(t == 0 ? Cfg::O_COL0 : Cfg::O_COL1);
+      if (warp == 4 && lane == 0) BLB_TRACE(gp + 1, 13);
+      const uint32_t o_addr = lane_addr + Cfg::O_COL;
       __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + t * QT + row) * D + h * HD;
       uint32_t r[32];
       uint32_t rx[16];
@@ -286,13 +321,15 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[t]);
+      if (lane == 0) mbar_arrive(o_empty);
+      if (warp == 4 && lane == 0) BLB_TRACE(gp + 1, 14);
     };
 
-    // exp2 + bf16 pack + swizzled store of one 32-column chunk; returns the chunk's partial row sum
+    // exp2 + bf16 pack of one 32-column chunk of S, stored as 16 packed columns of P in TMEM; returns the chunk's
+    // partial row sum
     auto exp_store = [&](const uint32_t (&r)[32], int c_global, float ms) -> float {
       float s0 = 0.f, s1 = 0.f;
-      uint8_t* prow = sP + (c_global >> 1) * (QT * 128) + row * 128;
+      uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         float p[8];
@@ -300,14 +337,12 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         for (int e = 0; e < 8; ++e) p[e] = ex2_approx(fmaf(__uint_as_float(r[j + e]), scale_log2, -ms));
         s0 += (p[0] + p[1]) + (p[2] + p[3]);
         s1 += (p[4] + p[5]) + (p[6] + p[7]);
-        uint4 pk;
-        pk.x = pack_bf16x2(p[0], p[1]);
-        pk.y = pack_bf16x2(p[2], p[3]);
-        pk.z = pack_bf16x2(p[4], p[5]);
-        pk.w = pack_bf16x2(p[6], p[7]);
-        const int chunk = ((c_global & 1) * 4 + (j >> 3)) << 4;   // 16-byte chunk inside the 64-key block row
-        *reinterpret_cast<uint4*>(prow + (chunk ^ sw128)) = pk;
+        pk[j / 2] = pack_bf16x2(p[0], p[1]);
+        pk[j / 2 + 1] = pack_bf16x2(p[2], p[3]);
+        pk[j / 2 + 2] = pack_bf16x2(p[4], p[5]);
+        pk[j / 2 + 3] = pack_bf16x2(p[6], p[7]);
       }
+      tmem_st_32x16(lane_addr + Cfg::P_COL + c_global * 16, pk);
       return s0 + s1;
     };
     auto max32 = [&](const uint32_t (&r)[32], float m) -> float {
@@ -325,6 +360,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     for (int g = 0; g < G; ++g) {
       mbar_wait(s_full, static_cast<uint32_t>(g & 1));
       tc_fence_after();
+      if (warp == 4 && lane == 0) BLB_TRACE(g, 8);
       // ---- pass 1: partial row max over this group's columns (TMEM loads one chunk ahead) ----
       float m = -INFINITY;
       {
@@ -351,11 +387,14 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
           if (KMAIN + j < T) m = fmaxf(m, __uint_as_float(r[j]));
       }
       xmax[wg * QT + row] = m;
+      if (warp == 4 && lane == 0) BLB_TRACE(g, 9);
       asm volatile("bar.sync 1, 256;" ::: "memory");    // the two groups exchange their partial maxima
+      if (warp == 4 && lane == 0) BLB_TRACE(g, 10);
       m = fmaxf(m, xmax[(wg ^ 1) * QT + row]);
       const float ms = m * scale_log2;
       // P(g-1) must have been consumed by PV(g-1) before it is overwritten
       if (g > 0) mbar_wait(p_empty, static_cast<uint32_t>((g - 1) & 1));
+      if (warp == 4 && lane == 0) BLB_TRACE(g, 11);
       // ---- pass 2: p = 2^(s*c - m*c), partial row sum, bf16 P into the swizzled A-operand layout ----
       float sum = 0.f;
       {
@@ -378,7 +417,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         uint32_t r[16];
         tmem_ld_32x16(lane_addr + KMAIN, r);
         tmem_ld_wait();
-        uint8_t* prow = sP + Cfg::P_MAIN + row * 32;
+        uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
           float p[8];
@@ -387,19 +426,19 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
             p[e] = (KMAIN + j + e < T) ? ex2_approx(fmaf(__uint_as_float(r[j + e]), scale_log2, -ms)) : 0.f;
             sum += p[e];
           }
-          uint4 pk;
-          pk.x = pack_bf16x2(p[0], p[1]);
-          pk.y = pack_bf16x2(p[2], p[3]);
-          pk.z = pack_bf16x2(p[4], p[5]);
-          pk.w = pack_bf16x2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(prow + (((j >> 3) << 4) ^ sw32)) = pk;
+          pk[j / 2] = pack_bf16x2(p[0], p[1]);
+          pk[j / 2 + 1] = pack_bf16x2(p[2], p[3]);
+          pk[j / 2 + 2] = pack_bf16x2(p[4], p[5]);
+          pk[j / 2 + 3] = pack_bf16x2(p[6], p[7]);
         }
+        tmem_st_32x8(lane_addr + Cfg::P_COL + 128, pk);
       }
       xsum[(g & 1) * 2 * QT + wg * QT + row] = sum;   // read by the other group in this tile's epilogue
-      fence_proxy_async_smem();     // make the generic-proxy P stores visible to the tensor core (async proxy)
-      tc_fence_before();            // and order our TMEM reads of S before the next S MMA
+      tmem_st_wait();               // P is in TMEM
+      tc_fence_before();            // order our TMEM reads of S / writes of P before the MMAs that follow p_full
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (warp == 4 && lane == 0) BLB_TRACE(g, 12);
       // ---- epilogue of the previous tile (its PV was issued right after P(g-1) became ready; the other group's
       //      partial sum of tile g-1 was published before this tile's bar.sync) ----
       if (g > 0) epilogue(g - 1, sum_prev);
@@ -453,6 +492,8 @@ int make_qkv_map(CUtensorMap* map, const void* qkv, int B, int T, int H, int hd,
   return r == CUDA_SUCCESS ? 0 : BLB_ERR_DRIVER;
 }
 
+long long* g_attn_trace = nullptr;
+
 template <int HD, int KX>
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream) {
   using Cfg = AttnCfg<HD, KX>;
@@ -473,12 +514,14 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
   const int grid = std::min(num_sms(), B * H);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * 256.0 * T * HD, stream);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, out, B, T, H, scale_log2);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, out, B, T, H, scale_log2, g_attn_trace);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
+
+void attention_set_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 
 // Handles query rows [0, 256) of every (image, head); returns BLB_ERR_SHAPE when (T, hd) is not one of the two
 // tower configurations this kernel is built for (the caller then uses the mma.sync kernel for everything).

@@ -188,6 +188,7 @@ const char* blb_status_string(int status) {
 
 long long blb_launch_count(void) { return launch_count(); }
 void blb_set_gemm_cta_group(int ctas) { gemm_set_cta_group(ctas); }
+void blb_debug_attention_trace(void* device_buffer) { attention_set_trace(static_cast<long long*>(device_buffer)); }
 void blb_timing_enable(int on) { timing_enable(on); }
 void blb_timing_reset(void) { timing_reset(); }
 int blb_timing_collect(int category, double* ms, double* work, long long* launches) {

@@ -63,6 +63,9 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
 // attention.cu — softmax(q kᵀ · hd^-0.5) v over packed qkv [B*T, 3*H*hd] → out [B*T, H*hd]
 int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream);
 
+// attention_tc.cu debug hook: CTA 0 writes clock64() stamps of pipeline events into this device buffer (or nullptr)
+void attention_set_trace(long long* device_buffer);
+
 // patch_embed.cu — im2col for Conv2d(3, D, 14, stride 14) and the cls/reg prefix rows
 int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int ldk, cudaStream_t stream);
 int write_prefix_tokens(const float* prefix, float* resid, int B, int T, int n_prefix, int D, cudaStream_t stream);

@@ -102,6 +102,10 @@ long long blb_launch_count(void);
 /* 0 = auto, 1 = cta_group::1 tiles (128xBN), 2 = cta_group::2 CTA pairs (256xBN) */
 void blb_set_gemm_cta_group(int ctas);
 
+/* Debug hook: device buffer of >= 128 int64 into which CTA 0 of the tcgen05 attention kernel records clock64()
+ * stamps of its pipeline events (tiles 8..15); NULL (default) disables it. */
+void blb_debug_attention_trace(void* device_buffer);
+
 /* Per-launch device timing for the roofline report (off by default).  When enabled every kernel launch is
  * bracketed by CUDA events on its stream; after the caller has synchronised, blb_timing_collect sums the elapsed
  * milliseconds, the algorithmic work (FLOPs for categories 0/1, bytes for 2/3) and the launch count of one

@@ -1,4 +1,4 @@
-// attention_tc.cu — tcgen05/TMEM softmax attention for the two towers (the v2 path of attention.cu).
+// attention_tc.cu — tcgen05/TMEM softmax attention for the two towers.
 //
 // timm Attention core: softmax(q·kᵀ·hd^-0.5)·v, no mask, 16 heads,
 //   DINOv2-reg4  T = 261 tokens, head_dim 64   →  template <64, 16>  (256 keys + 16-key tail block, 5 of them real)
@@ -6,16 +6,19 @@
 // One persistent CTA per SM walks (image, head) units; per unit it handles the first 256 query rows as two
 // 128-row tiles (the T-256 remaining query rows of DINOv2 go to the mma.sync kernel in attention.cu).
 //
-//   warp 0    TMA producer: Q tiles, K, V straight out of the packed QKV GEMM output through a 4-D tensor map
-//             {d, 3·H head slots, token, image}; rows >= T and d >= head_dim are zero-filled by TMA (OOB)
-//   warp 1    MMA issuer:   S = Q·Kᵀ  (M128 × N256[+16], fp32 in TMEM columns [0,272))
-//                           O = P·V   (A = P from shared memory, B = V as an MN-major operand, TMEM [320,..))
-//   warp 2    TMEM allocator
-//   warps 4-11 softmax + epilogue: two groups of 4 warps split the S columns; a thread owns query row = TMEM lane:
-//             row max, exp2, row sum in fp32 (partials combined through smem), P rounded to bf16 into 128B-swizzled
-//             shared memory (the UMMA A-operand layout), then O / rowsum → bf16 → global
-// Issue order per tile g:  S(g) → [softmax(g) on the SIMT side ‖ PV(g-1) on the tensor pipe] → S(g+1) …
-// so the tensor pipe only ever exposes one Q·Kᵀ (~550 cycles) per ~2300-cycle MUFU-bound softmax.
+//   warp 8     TMA producer: Q tiles, K, V straight out of the packed QKV GEMM output through a 4-D tensor map
+//              {d, 3·H head slots, token, image}; rows >= T and d >= head_dim are zero-filled by TMA (OOB);
+//              K and V are double-buffered across units
+//   warp 9     MMA issuer:   S = Q·Kᵀ  (SS: M128 × N256[+16], fp32 in TMEM columns [0, 256+KX))
+//                            O = P·V   (TS: A = bf16 P in TMEM, B = V as an MN-major smem operand)
+//   warp 10    TMEM allocator   (control warps carry the highest ids: the sub-partition arbiter prefers the highest
+//              eligible warp id, so TMA / MMA issue never queues behind the MUFU-bound softmax warps)
+//   warps 0-7  softmax + epilogue: two groups of 4 warps split the S columns; a thread owns query row = TMEM lane.
+//              It pulls its whole slice of the S row into registers with ONE pass of tcgen05.ld and releases S at
+//              once (s_free) — the next tile's Q·Kᵀ runs on the tensor pipe underneath this tile's softmax — then
+//              row max (partials combined through smem), exp2, row sum in fp32, P rounded to bf16 and written back
+//              to TMEM with tcgen05.st, and finally O / rowsum → bf16 → global for the previous tile.
+//   TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [.., +(256+KX)/2) | O fp32 [.., +64/80)
 #include <algorithm>
 #include <cmath>
 
@@ -106,179 +109,226 @@ struct AttnCfg {
   static constexpr int KV_BYTES = KV_MAIN + KV_TAIL + KV_X;
   static constexpr int OFF_Q0 = 0;
   static constexpr int OFF_Q1 = OFF_Q0 + Q_BYTES;
-  static constexpr int OFF_K = OFF_Q1 + Q_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_BYTES;
-  static constexpr int OFF_XCHG = OFF_V + KV_BYTES;              // row max [2][128] + row sums [2][2][128] (fp32)
-  static constexpr int OFF_BAR = OFF_XCHG + 6 * QT * 4;
+  static constexpr int OFF_K = OFF_Q1 + Q_BYTES;                 // [2 unit parities]
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;             // [2 unit parities]
+  static constexpr int OFF_XCHG = OFF_V + 2 * KV_BYTES;          // row max [2][128] + row sums [2][2][128] (fp32)
+  static constexpr int OFF_OST = OFF_XCHG + 6 * QT * 4;          // per-warp [32 rows x 64 B] output staging chunks
+  static constexpr int OFF_BAR = OFF_OST + 8 * 2048;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [P_COL, P_COL + (256+KX)/2) | O fp32 [O_COL, O_COL + HDP)
   static constexpr int S_COLS = KMAIN + KX;
   static constexpr int P_COL = S_COLS;
   static constexpr int P_COLS = S_COLS / 2;
   static constexpr int O_COL = P_COL + P_COLS;
+  static constexpr int NREG_S = 128 + KX / 2;                    // S columns one softmax thread keeps in registers
   static_assert(Q_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0 && KV_MAIN % 1024 == 0, "1 KB aligned blocks");
   static_assert(O_COL + HDP <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
 struct AttnMaps {
   CUtensorMap q_main, kv_main, kv_tail, q_x, kv_x;
 };
 
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <int HD, int KX>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out, int B, int T, int H,
                     float scale_log2, long long* trace) {
   // trace (debug only, normally nullptr): CTA 0 records clock64() at pipeline events of tiles [8, 16):
-  // trace[(g-8)*16 + e]; e: 0 mma:p_full seen, 1 mma:S issued, 2 mma:PV waits done, 3 mma:PV issued,
-  //                         8 sm:s_full seen, 9 sm:pass1 done, 10 sm:bar done, 11 sm:p_empty seen, 12 sm:pass2 done,
-  //                         13 sm:epilogue o_full seen, 14 sm:epilogue done
+  // trace[(g-8)*16 + e]; e: 0 mma:s_free(g) seen, 1 mma:S(g+1) issued, 2 mma:p_full(g)+o_empty seen, 3 mma:PV(g) issued,
+  //   8 sm:s_full seen, 9 sm:S in registers (s_free), 10 sm:max exchanged, 11 sm:p_empty seen, 12 sm:P stored/p_full,
+  //   13 sm:epilogue o_full seen, 14 sm:epilogue done
 #define BLB_TRACE(g_, e_)                                                                   \
   do {                                                                                      \
-    if (trace != nullptr && blockIdx.x == 0 && (g_) >= 8 && (g_) < 16) trace[((g_) - 8) * 16 + (e_)] = clock64(); \
+    if (trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (g_) >= 8 && (g_) < 16)            \
+      trace[((g_) - 8) * 16 + (e_)] = clock64();                                                                \
   } while (0)
   using Cfg = AttnCfg<HD, KX>;
   extern __shared__ uint8_t smem_raw_attn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_full = bars;         // [2 tiles of a unit]
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* k_full = bars + 4;
-  uint64_t* k_empty = bars + 5;
-  uint64_t* v_full = bars + 6;
-  uint64_t* v_empty = bars + 7;
-  uint64_t* s_full = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 10;
-  uint64_t* o_full = bars + 11;
-  uint64_t* o_empty = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* k_full = bars + 4;     // [2 unit parities]
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;     // [2]
+  uint64_t* v_empty = bars + 10;   // [2]
+  uint64_t* s_full = bars + 12;    // MMA → softmax: S(g) is in TMEM
+  uint64_t* s_free = bars + 13;    // softmax → MMA: S(g) is in registers, TMEM columns reusable
+  uint64_t* p_full = bars + 14;    // softmax → MMA: P(g) is in TMEM
+  uint64_t* p_empty = bars + 15;   // MMA → softmax: PV(g) has consumed P(g)
+  uint64_t* o_full = bars + 16;    // MMA → epilogue
+  uint64_t* o_empty = bars + 17;   // epilogue → MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr int W_TMA = 8, W_MMA = 9, W_ALLOC = 10;
   const int n_units = B * H;
   const int my_units = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const int G = 2 * my_units;      // tiles this CTA processes
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&maps.q_main);
     tma_prefetch_desc(&maps.kv_main);
     if (KX > 0) tma_prefetch_desc(&maps.kv_tail);
     if (Cfg::SPLIT_D) { tma_prefetch_desc(&maps.q_x); tma_prefetch_desc(&maps.kv_x); }
   }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(p_empty, 1);
+  if (warp == W_MMA && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(p_full, 8); mbar_init(p_empty, 1);
     mbar_init(o_full, 1); mbar_init(o_empty, 8);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_slot, 512);
+  if (warp == W_ALLOC) tmem_alloc<1>(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   uint8_t* sQ[2] = {smem + Cfg::OFF_Q0, smem + Cfg::OFF_Q1};
-  uint8_t* sK = smem + Cfg::OFF_K;
-  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sK[2] = {smem + Cfg::OFF_K, smem + Cfg::OFF_K + Cfg::KV_BYTES};
+  uint8_t* sV[2] = {smem + Cfg::OFF_V, smem + Cfg::OFF_V + Cfg::KV_BYTES};
 
-  if (warp == 0) {
-    // ============================== TMA producer ===================================================
-    if (lane == 0) {
-      for (int i = 0; i < my_units; ++i) {
-        const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
-        const int b = u / H, h = u - b * H;
-        const uint32_t ph = static_cast<uint32_t>(i & 1);
-        mbar_wait(k_empty, ph ^ 1u);
-        mbar_expect_tx(k_full, Cfg::KV_BYTES);
-        tma_load_4d(sK, &maps.kv_main, k_full, 0, H + h, 0, b);
-        if (KX > 0) tma_load_4d(sK + Cfg::KV_MAIN, &maps.kv_tail, k_full, 0, H + h, KMAIN, b);
-        if (Cfg::SPLIT_D) tma_load_4d(sK + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, k_full, 64, H + h, 0, b);
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&q_empty[t], ph ^ 1u);
-          mbar_expect_tx(&q_full[t], Cfg::Q_BYTES);
-          tma_load_4d(sQ[t], &maps.q_main, &q_full[t], 0, h, t * QT, b);
-          if (Cfg::SPLIT_D) tma_load_4d(sQ[t] + Cfg::Q_MAIN, &maps.q_x, &q_full[t], 64, h, t * QT, b);
+  if (warp >= 8) {
+    setmaxnreg_dec<56>();          // hand registers to the softmax warps
+    if (warp == W_TMA) {
+      // ============================== TMA producer (warp-uniform loop, one elected lane issues) ===========
+      {
+        for (int i = 0; i < my_units; ++i) {
+          const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+          const int b = u / H, h = u - b * H;
+          const int kb = i & 1;                                          // K/V buffer of this unit
+          const uint32_t ph = static_cast<uint32_t>(i & 1);              // Q barriers: one use per unit
+          const uint32_t kph = static_cast<uint32_t>((i >> 1) & 1);      // K/V barriers: one use per two units
+          mbar_wait(&k_empty[kb], kph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&k_full[kb], Cfg::KV_BYTES);
+            tma_load_4d(sK[kb], &maps.kv_main, &k_full[kb], 0, H + h, 0, b);
+            if (KX > 0) tma_load_4d(sK[kb] + Cfg::KV_MAIN, &maps.kv_tail, &k_full[kb], 0, H + h, KMAIN, b);
+            if (Cfg::SPLIT_D)
+              tma_load_4d(sK[kb] + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, &k_full[kb], 64, H + h, 0, b);
+          }
+          __syncwarp();
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&q_empty[t], ph ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(&q_full[t], Cfg::Q_BYTES);
+              tma_load_4d(sQ[t], &maps.q_main, &q_full[t], 0, h, t * QT, b);
+              if (Cfg::SPLIT_D) tma_load_4d(sQ[t] + Cfg::Q_MAIN, &maps.q_x, &q_full[t], 64, h, t * QT, b);
+            }
+            __syncwarp();
+          }
+          mbar_wait(&v_empty[kb], kph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&v_full[kb], Cfg::KV_BYTES);
+            tma_load_4d(sV[kb], &maps.kv_main, &v_full[kb], 0, 2 * H + h, 0, b);
+            if (KX > 0) tma_load_4d(sV[kb] + Cfg::KV_MAIN, &maps.kv_tail, &v_full[kb], 0, 2 * H + h, KMAIN, b);
+            if (Cfg::SPLIT_D)
+              tma_load_4d(sV[kb] + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, &v_full[kb], 64, 2 * H + h, 0, b);
+          }
+          __syncwarp();
         }
-        mbar_wait(v_empty, ph ^ 1u);
-        mbar_expect_tx(v_full, Cfg::KV_BYTES);
-        tma_load_4d(sV, &maps.kv_main, v_full, 0, 2 * H + h, 0, b);
-        if (KX > 0) tma_load_4d(sV + Cfg::KV_MAIN, &maps.kv_tail, v_full, 0, 2 * H + h, KMAIN, b);
-        if (Cfg::SPLIT_D) tma_load_4d(sV + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, v_full, 64, 2 * H + h, 0, b);
       }
-    }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ====================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s_main = idesc_bf16(QT, KMAIN, 0);
-      constexpr uint32_t idesc_s_tail = idesc_bf16(QT, 16, 0);
-      constexpr uint32_t idesc_o_main = idesc_bf16(QT, 64, 1);
-      constexpr uint32_t idesc_o_x = idesc_bf16(QT, 16, 1);
-      for (int g = 0; g <= G; ++g) {
-        if (g > 0) {   // softmax(g-1) has read S and written P(g-1)
-          mbar_wait(p_full, static_cast<uint32_t>((g - 1) & 1));
+    } else if (warp == W_MMA) {
+      // =============================== MMA issuer (warp-uniform loop, one elected lane issues) ===========
+      {
+        constexpr uint32_t idesc_s_main = idesc_bf16(QT, KMAIN, 0);
+        constexpr uint32_t idesc_s_tail = idesc_bf16(QT, 16, 0);
+        constexpr uint32_t idesc_o_main = idesc_bf16(QT, 64, 1);
+        constexpr uint32_t idesc_o_x = idesc_bf16(QT, 16, 1);
+        // S(g) = Q·Kᵀ into TMEM columns [0, 256+KX)
+        auto issue_s = [&](int g) {
+          const int t = g & 1, i = g >> 1, kb = i & 1;
+          if (t == 0) mbar_wait(&k_full[kb], static_cast<uint32_t>((i >> 1) & 1));
+          mbar_wait(&q_full[t], static_cast<uint32_t>(i & 1));
           tc_fence_after();
-          BLB_TRACE(g, 0);
-        }
-        if (g < G) {
-          // ---------------- S(g) = Q · Kᵀ ----------------
-          const int t = g & 1, i = g >> 1;
-          const uint32_t ph = static_cast<uint32_t>(i & 1);
-          if (t == 0) mbar_wait(k_full, ph);
-          mbar_wait(&q_full[t], ph);
-          tc_fence_after();
-          const uint32_t qa = smem_u32(sQ[t]), ka = smem_u32(sK);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16<1>(tmem_base, make_desc(qa, 1024, 2) + 2 * k, make_desc(ka, 1024, 2) + 2 * k, idesc_s_main,
-                         k > 0 ? 1u : 0u);
-          if (Cfg::SPLIT_D)
-            umma_bf16<1>(tmem_base, make_desc(qa + Cfg::Q_MAIN, 256, 6),
-                         make_desc(ka + Cfg::KV_MAIN + Cfg::KV_TAIL, 256, 6), idesc_s_main, 1u);
-          if (KX > 0) {
+          if (elect_one()) {
+            const uint32_t qa = smem_u32(sQ[t]), ka = smem_u32(sK[kb]);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16<1>(tmem_base + KMAIN, make_desc(qa, 1024, 2) + 2 * k,
-                           make_desc(ka + Cfg::KV_MAIN, 1024, 2) + 2 * k, idesc_s_tail, k > 0 ? 1u : 0u);
+              umma_bf16<1>(tmem_base, make_desc(qa, 1024, 2) + 2 * k, make_desc(ka, 1024, 2) + 2 * k, idesc_s_main,
+                           k > 0 ? 1u : 0u);
+            if (Cfg::SPLIT_D)
+              umma_bf16<1>(tmem_base, make_desc(qa + Cfg::Q_MAIN, 256, 6),
+                           make_desc(ka + Cfg::KV_MAIN + Cfg::KV_TAIL, 256, 6), idesc_s_main, 1u);
+            if (KX > 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16<1>(tmem_base + KMAIN, make_desc(qa, 1024, 2) + 2 * k,
+                             make_desc(ka + Cfg::KV_MAIN, 1024, 2) + 2 * k, idesc_s_tail, k > 0 ? 1u : 0u);
+            }
+            umma_commit<1>(s_full);
+            umma_commit<1>(&q_empty[t]);
+            if (t == 1) umma_commit<1>(&k_empty[kb]);
           }
-          umma_commit<1>(s_full);
-          BLB_TRACE(g, 1);
-          umma_commit<1>(&q_empty[t]);
-          if (t == 1) umma_commit<1>(k_empty);
-        }
-        if (g > 0) {
-          // ---------------- O(g-1) = P(g-1) · V   (A = P in TMEM, B = V as an MN-major smem operand) ----------------
-          const int gp = g - 1, t = gp & 1, i = gp >> 1;
-          const uint32_t ph = static_cast<uint32_t>(i & 1);
-          if (t == 0) mbar_wait(v_full, ph);
-          mbar_wait(o_empty, static_cast<uint32_t>(gp & 1) ^ 1u);   // epilogue(g-2) drained the O accumulator
+          __syncwarp();
+        };
+        if (G > 0) issue_s(0);
+        for (int g = 0; g < G; ++g) {
+          if (g + 1 < G) {
+            // softmax(g) holds S(g) in registers → the next Q·Kᵀ runs underneath this tile's softmax
+            mbar_wait(s_free, static_cast<uint32_t>(g & 1));
+            tc_fence_after();
+            BLB_TRACE(g, 0);
+            issue_s(g + 1);
+            BLB_TRACE(g, 1);
+          }
+          // ---------------- O(g) = P(g) · V   (A = P in TMEM, B = V as an MN-major smem operand) ----------------
+          const int t = g & 1, i = g >> 1, kb = i & 1;
+          mbar_wait(p_full, static_cast<uint32_t>(g & 1));
+          if (t == 0) mbar_wait(&v_full[kb], static_cast<uint32_t>((i >> 1) & 1));
+          mbar_wait(o_empty, static_cast<uint32_t>(g & 1) ^ 1u);   // epilogue(g-1) drained the O accumulator
           tc_fence_after();
           BLB_TRACE(g, 2);
-          const uint32_t o_col = tmem_base + Cfg::O_COL;
-          const uint32_t p_col = tmem_base + Cfg::P_COL;
-          const uint32_t va = smem_u32(sV);
+          if (elect_one()) {
+            const uint32_t o_col = tmem_base + Cfg::O_COL;
+            const uint32_t p_col = tmem_base + Cfg::P_COL;
+            const uint32_t va = smem_u32(sV[kb]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {   // 16 keys per step: 8 packed P columns, V rows 16j..16j+15
-            umma_bf16_ts(o_col, p_col + j * 8, make_desc(va + j * 2048, 1024, 2), idesc_o_main, j > 0 ? 1u : 0u);
-            if (Cfg::SPLIT_D)
-              umma_bf16_ts(o_col + 64, p_col + j * 8, make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6),
-                           idesc_o_x, j > 0 ? 1u : 0u);
+            for (int j = 0; j < 16; ++j) {   // 16 keys per step: 8 packed P columns, V rows 16j..16j+15
+              umma_bf16_ts(o_col, p_col + j * 8, make_desc(va + j * 2048, 1024, 2), idesc_o_main, j > 0 ? 1u : 0u);
+              if (Cfg::SPLIT_D)
+                umma_bf16_ts(o_col + 64, p_col + j * 8,
+                             make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6), idesc_o_x, j > 0 ? 1u : 0u);
+            }
+            if (KX > 0)
+              umma_bf16_ts(o_col, p_col + 128, make_desc(va + Cfg::KV_MAIN, 1024, 2), idesc_o_main, 1u);
+            umma_commit<1>(p_empty);
+            umma_commit<1>(o_full);
+            if (t == 1) umma_commit<1>(&v_empty[kb]);
           }
-          if (KX > 0)
-            umma_bf16_ts(o_col, p_col + 128, make_desc(va + Cfg::KV_MAIN, 1024, 2), idesc_o_main, 1u);
-          umma_commit<1>(p_empty);
+          __syncwarp();
           BLB_TRACE(g, 3);
-          umma_commit<1>(o_full);
-          if (t == 1) umma_commit<1>(v_empty);
         }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ============================ softmax + epilogue ===============================================
-    // 8 warps: warp-group wg = 0/1 owns S columns [0,128) / [128, 256+KX); both groups see all 128 rows
-    // (warps w and w+4 share TMEM lane quarter w%4), so every SM sub-partition runs two softmax warps whose
-    // TMEM-load / MUFU / shared-store latencies overlap.  Row max and row sum are combined through shared memory.
+    // 8 warps: group wg = 0/1 owns S columns [128·wg, 128·wg+128) plus 8 of the 16 tail columns; both groups see
+    // all 128 rows (warps w and w+4 share TMEM lane quarter w%4), i.e. two softmax warps per SM sub-partition.
+    setmaxnreg_inc<216>();
     const int q = warp & 3;
-    const int wg = (warp - 4) >> 2;
+    const int wg = warp >> 2;
     const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int D = H * HD;
@@ -286,6 +336,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     float* xsum = xmax + 2 * QT;                                             // [2 tile parities][2 groups][128]
     float sum_prev = 0.f;
     const int col_base = wg * 128;
+    const int tail_key0 = KMAIN + wg * 8;                // first key of this group's 8 tail columns
 
     auto epilogue = [&](int gp, float own_sum) {
       const int t = gp & 1, i = gp >> 1;
@@ -294,7 +345,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       const float inv = 1.0f / (own_sum + xsum[(gp & 1) * 2 * QT + (wg ^ 1) * QT + row]);
       mbar_wait(o_full, static_cast<uint32_t>(gp & 1));
       tc_fence_after();
-      if (warp == 4 && lane == 0) BLB_TRACE(gp + 1, 13);
+      if (warp == 0 && lane == 0) BLB_TRACE(gp + 1, 13);
       const uint32_t o_addr = lane_addr + Cfg::O_COL;
       __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + t * QT + row) * D + h * HD;
       uint32_t r[32];
@@ -302,15 +353,32 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       tmem_ld_32x32(o_addr + wg * 32, r);               // this group's 32 of the 64 main O columns
       if (Cfg::SPLIT_D && wg == 1) tmem_ld_32x16(o_addr + 64, rx);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);              // O is in registers: PV(g) may overwrite the accumulator
+      // stage the lane's 64-byte row slice in smem (16-byte piece j at j ^ ((row>>1)&3): conflict-free both ways),
+      // then store transposed so that one instruction writes 8 rows x 64 contiguous bytes instead of 32 x 16
+      uint8_t* ob = smem + Cfg::OFF_OST + warp * 2048;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < 4; ++j) {
         uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(r[j + 4]) * inv, __uint_as_float(r[j + 5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(r[j + 6]) * inv, __uint_as_float(r[j + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + wg * 32 + j) = pk;
+        pk.x = pack_bf16x2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(ob + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
       }
+      __syncwarp();
+      {
+        __nv_bfloat16* slab = out + (static_cast<size_t>(b) * T + t * QT + q * 32) * D + h * HD + wg * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rr = k * 8 + (lane >> 2), j = lane & 3;
+          const uint4 pk = *reinterpret_cast<const uint4*>(ob + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(slab + static_cast<size_t>(rr) * D + j * 8) = pk;
+        }
+      }
+      __syncwarp();
       if (Cfg::SPLIT_D && wg == 1) {
         uint4 pk;
         pk.x = pack_bf16x2(__uint_as_float(rx[0]) * inv, __uint_as_float(rx[1]) * inv);
@@ -319,128 +387,86 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         pk.w = pack_bf16x2(__uint_as_float(rx[6]) * inv, __uint_as_float(rx[7]) * inv);
         *reinterpret_cast<uint4*>(dst + 64) = pk;        // d 64..71 (72..79 are padding)
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
-      if (warp == 4 && lane == 0) BLB_TRACE(gp + 1, 14);
-    };
-
-    // exp2 + bf16 pack of one 32-column chunk of S, stored as 16 packed columns of P in TMEM; returns the chunk's
-    // partial row sum
-    auto exp_store = [&](const uint32_t (&r)[32], int c_global, float ms) -> float {
-      float s0 = 0.f, s1 = 0.f;
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float p[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) p[e] = ex2_approx(fmaf(__uint_as_float(r[j + e]), scale_log2, -ms));
-        s0 += (p[0] + p[1]) + (p[2] + p[3]);
-        s1 += (p[4] + p[5]) + (p[6] + p[7]);
-        pk[j / 2] = pack_bf16x2(p[0], p[1]);
-        pk[j / 2 + 1] = pack_bf16x2(p[2], p[3]);
-        pk[j / 2 + 2] = pack_bf16x2(p[4], p[5]);
-        pk[j / 2 + 3] = pack_bf16x2(p[6], p[7]);
-      }
-      tmem_st_32x16(lane_addr + Cfg::P_COL + c_global * 16, pk);
-      return s0 + s1;
-    };
-    auto max32 = [&](const uint32_t (&r)[32], float m) -> float {
-      float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        m0 = fmaxf(m0, __uint_as_float(r[j]));
-        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
-        m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
-        m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
-      }
-      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      if (warp == 0 && lane == 0) BLB_TRACE(gp + 1, 14);
     };
 
     for (int g = 0; g < G; ++g) {
       mbar_wait(s_full, static_cast<uint32_t>(g & 1));
       tc_fence_after();
-      if (warp == 4 && lane == 0) BLB_TRACE(g, 8);
-      // ---- pass 1: partial row max over this group's columns (TMEM loads one chunk ahead) ----
-      float m = -INFINITY;
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(lane_addr + col_base, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(lane_addr + col_base + 32, rb);
-        m = max32(ra, m);
-        tmem_ld_wait();
-        tmem_ld_32x32(lane_addr + col_base + 64, ra);
-        m = max32(rb, m);
-        tmem_ld_wait();
-        tmem_ld_32x32(lane_addr + col_base + 96, rb);
-        m = max32(ra, m);
-        tmem_ld_wait();
-        m = max32(rb, m);
-      }
-      if (KX > 0 && wg == 1) {
-        uint32_t r[16];
-        tmem_ld_32x16(lane_addr + KMAIN, r);
-        tmem_ld_wait();
+      if (warp == 0 && lane == 0) BLB_TRACE(g, 8);
+      // ---- this thread's slice of the S row → registers in one pass, then release S ----
+      uint32_t sv[Cfg::NREG_S];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (KMAIN + j < T) m = fmaxf(m, __uint_as_float(r[j]));
+      for (int c = 0; c < 4; ++c)
+        tmem_ld_32x32(lane_addr + col_base + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[c * 32]));
+      if (KX > 0) tmem_ld_32x8(lane_addr + tail_key0, reinterpret_cast<uint32_t(&)[8]>(sv[128]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      if (warp == 0 && lane == 0) BLB_TRACE(g, 9);
+      // ---- row max ----
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 128; j += 4) {
+        m0 = fmaxf(m0, __uint_as_float(sv[j]));
+        m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+        m2 = fmaxf(m2, __uint_as_float(sv[j + 2]));
+        m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
       }
+      if (KX > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (tail_key0 + j < T) m0 = fmaxf(m0, __uint_as_float(sv[128 + j]));
+      }
+      float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       xmax[wg * QT + row] = m;
-      if (warp == 4 && lane == 0) BLB_TRACE(g, 9);
       asm volatile("bar.sync 1, 256;" ::: "memory");    // the two groups exchange their partial maxima
-      if (warp == 4 && lane == 0) BLB_TRACE(g, 10);
       m = fmaxf(m, xmax[(wg ^ 1) * QT + row]);
       const float ms = m * scale_log2;
+      if (warp == 0 && lane == 0) BLB_TRACE(g, 10);
       // P(g-1) must have been consumed by PV(g-1) before it is overwritten
       if (g > 0) mbar_wait(p_empty, static_cast<uint32_t>((g - 1) & 1));
-      if (warp == 4 && lane == 0) BLB_TRACE(g, 11);
-      // ---- pass 2: p = 2^(s*c - m*c), partial row sum, bf16 P into the swizzled A-operand layout ----
-      float sum = 0.f;
-      {
-        uint32_t ra[32], rb[32];
-        const int c0 = wg * 4;
-        tmem_ld_32x32(lane_addr + col_base, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(lane_addr + col_base + 32, rb);
-        sum += exp_store(ra, c0, ms);
-        tmem_ld_wait();
-        tmem_ld_32x32(lane_addr + col_base + 64, ra);
-        sum += exp_store(rb, c0 + 1, ms);
-        tmem_ld_wait();
-        tmem_ld_32x32(lane_addr + col_base + 96, rb);
-        sum += exp_store(ra, c0 + 2, ms);
-        tmem_ld_wait();
-        sum += exp_store(rb, c0 + 3, ms);
-      }
-      if (KX > 0 && wg == 1) {
-        uint32_t r[16];
-        tmem_ld_32x16(lane_addr + KMAIN, r);
-        tmem_ld_wait();
-        uint32_t pk[8];
+      if (warp == 0 && lane == 0) BLB_TRACE(g, 11);
+      // ---- p = 2^(s*c - m*c), partial row sum, bf16 P → TMEM (16 packed columns per 32 keys) ----
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-          float p[8];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            p[e] = (KMAIN + j + e < T) ? ex2_approx(fmaf(__uint_as_float(r[j + e]), scale_log2, -ms)) : 0.f;
-            sum += p[e];
-          }
-          pk[j / 2] = pack_bf16x2(p[0], p[1]);
-          pk[j / 2 + 1] = pack_bf16x2(p[2], p[3]);
-          pk[j / 2 + 2] = pack_bf16x2(p[4], p[5]);
-          pk[j / 2 + 3] = pack_bf16x2(p[6], p[7]);
+        for (int j = 0; j < 32; j += 4) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j]), scale_log2, -ms));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j + 1]), scale_log2, -ms));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j + 2]), scale_log2, -ms));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j + 3]), scale_log2, -ms));
+          s0 += p0 + p1;
+          s1 += p2 + p3;
+          pk[j / 2] = pack_bf16x2(p0, p1);
+          pk[j / 2 + 1] = pack_bf16x2(p2, p3);
         }
-        tmem_st_32x8(lane_addr + Cfg::P_COL + 128, pk);
+        tmem_st_32x16(lane_addr + Cfg::P_COL + (col_base + c * 32) / 2, pk);
       }
+      if (KX > 0) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float p0 = (tail_key0 + j < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j]), scale_log2, -ms)) : 0.f;
+          const float p1 =
+              (tail_key0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j + 1]), scale_log2, -ms)) : 0.f;
+          s0 += p0 + p1;
+          pk[j / 2] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x4(lane_addr + Cfg::P_COL + tail_key0 / 2, pk);
+      }
+      const float sum = s0 + s1;
       xsum[(g & 1) * 2 * QT + wg * QT + row] = sum;   // read by the other group in this tile's epilogue
       tmem_st_wait();               // P is in TMEM
-      tc_fence_before();            // order our TMEM reads of S / writes of P before the MMAs that follow p_full
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      if (warp == 4 && lane == 0) BLB_TRACE(g, 12);
-      // ---- epilogue of the previous tile (its PV was issued right after P(g-1) became ready; the other group's
-      //      partial sum of tile g-1 was published before this tile's bar.sync) ----
+      if (warp == 0 && lane == 0) BLB_TRACE(g, 12);
+      // ---- epilogue of the previous tile (its PV ran underneath this tile's softmax; the other group's partial
+      //      sum of tile g-1 was published before this tile's bar.sync) ----
       if (g > 0) epilogue(g - 1, sum_prev);
       sum_prev = sum;
     }
@@ -452,7 +478,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }

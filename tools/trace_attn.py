@@ -5,9 +5,9 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from bridgelang_b200 import _lib, ops
 
-NAMES = {0: "mma:p_full(g-1) seen", 1: "mma:S(g) issued", 2: "mma:PV(g-1) waits done", 3: "mma:PV(g-1) issued",
-         8: "sm:s_full(g) seen", 9: "sm:pass1 done", 10: "sm:bar done", 11: "sm:p_empty(g-1) seen",
-         12: "sm:pass2 done/p_full(g)", 13: "sm:o_full(g-1) seen", 14: "sm:epilogue(g-1) done"}
+NAMES = {0: "mma:s_free(g) seen", 1: "mma:S(g+1) issued", 2: "mma:p_full(g)+o_empty seen", 3: "mma:PV(g) issued",
+         8: "sm:s_full(g) seen", 9: "sm:S in regs / s_free", 10: "sm:max exchanged", 11: "sm:p_empty(g-1) seen",
+         12: "sm:P stored / p_full(g)", 13: "sm:o_full(g-1) seen", 14: "sm:epilogue(g-1) done"}
 for (B, T, H, hd) in ((256, 261, 16, 64), (256, 256, 16, 72)):
     qkv = torch.randn(B * T, 3 * H * hd, device="cuda").bfloat16()
     buf = torch.zeros(256, dtype=torch.int64, device="cuda")

@@ -358,7 +358,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       if (lane == 0) mbar_arrive(o_empty);              // O is in registers: PV(g) may overwrite the accumulator
       // stage the lane's 64-byte row slice in smem (16-byte piece j at j ^ ((row>>1)&3): conflict-free both ways),
       // then store transposed so that one instruction writes 8 rows x 64 contiguous bytes instead of 32 x 16
-      uint8_t* ob = smem + Cfg::OFF_OST + warp * 2048;
+      const uint32_t ob = smem_u32(smem + Cfg::OFF_OST) + warp * 2048;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 pk;
@@ -366,16 +366,21 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         pk.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
         pk.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
         pk.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-        *reinterpret_cast<uint4*>(ob + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+        sts128(ob + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk);
       }
       __syncwarp();
       {
         __nv_bfloat16* slab = out + (static_cast<size_t>(b) * T + t * QT + q * 32) * D + h * HD + wg * 32;
+        uint4 tv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int rr = k * 8 + (lane >> 2), j = lane & 3;
-          const uint4 pk = *reinterpret_cast<const uint4*>(ob + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
-          *reinterpret_cast<uint4*>(slab + static_cast<size_t>(rr) * D + j * 8) = pk;
+          tv[k] = lds128(ob + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int rr = k * 8 + (lane >> 2), j = lane & 3;
+          stg128(slab + static_cast<size_t>(rr) * D + j * 8, tv[k]);
         }
       }
       __syncwarp();

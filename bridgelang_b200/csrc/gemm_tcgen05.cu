@@ -246,7 +246,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           t_dst[k] = ok ? static_cast<long long>(dr) * epi.ld_out + epi.out_col_off : -1;
         }
       }
-      uint8_t* obuf = smem_r + ew * OCHUNK_BYTES;
+      const uint32_t obuf_s = smem_u32(smem_r) + ew * OCHUNK_BYTES;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -262,11 +262,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (RTMA) {
           // this lane's row of the TMA-staged residual chunk (128-byte rows, 128B-swizzled → conflict-free)
           mbar_wait(&rbar[seq & 1], static_cast<uint32_t>((seq >> 1) & 1));
-          const uint8_t* src = rbuf + (seq & 1) * RCHUNK_BYTES + lane * 128;
+          const uint32_t src = smem_u32(rbuf) + (seq & 1) * RCHUNK_BYTES + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 x4 = *reinterpret_cast<const float4*>(src + ((j ^ (lane & 7)) << 4));
-            xres[4 * j] = x4.x; xres[4 * j + 1] = x4.y; xres[4 * j + 2] = x4.z; xres[4 * j + 3] = x4.w;
+            const uint4 x4 = lds128(src + ((j ^ (lane & 7)) << 4));
+            xres[4 * j] = __uint_as_float(x4.x); xres[4 * j + 1] = __uint_as_float(x4.y);
+            xres[4 * j + 2] = __uint_as_float(x4.z); xres[4 * j + 3] = __uint_as_float(x4.w);
           }
         }
         tmem_ld_wait();
@@ -294,16 +295,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
             pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
             pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(obuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+            sts128(obuf_s + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk);
           }
           __syncwarp();
           // transposed read → each store instruction now writes 8 rows x 64 contiguous bytes
+          uint4 tv[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = k * 8 + (lane >> 2), j = lane & 3;
-            const uint4 pk = *reinterpret_cast<const uint4*>(obuf + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
-            if (t_dst[k] >= 0) *reinterpret_cast<uint4*>(epi.out + t_dst[k] + col0 + j * 8) = pk;
+            tv[k] = lds128(obuf_s + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (t_dst[k] >= 0) stg128(epi.out + t_dst[k] + col0 + (lane & 3) * 8, tv[k]);
           __syncwarp();
         } else if constexpr (MODE == EPI_PATCH) {
           // out_f32[dst_row, col] = acc + bias + pos_embed[token, col]   (timm PatchEmbed + _pos_embed)
@@ -352,18 +356,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if constexpr (RTMA) {
             // write the updated row back into the (already consumed) residual chunk in place, then store the
             // chunk transposed: each store instruction writes 4 rows x 128 contiguous bytes
-            uint8_t* cb = rbuf + ((seq) & 1) * RCHUNK_BYTES;
+            const uint32_t cb = smem_u32(rbuf) + (seq & 1) * RCHUNK_BYTES;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(cb + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              sts128(cb + lane * 128 + ((j ^ (lane & 7)) << 4),
+                     make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                __float_as_uint(v[4 * j + 3])));
             __syncwarp();
+            uint4 tv[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const int r = k * 4 + (lane >> 3), j = lane & 7;
-              const float4 x4 = *reinterpret_cast<const float4*>(cb + r * 128 + ((j ^ (r & 7)) << 4));
+              tv[k] = lds128(cb + r * 128 + ((j ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int r = k * 4 + (lane >> 3), j = lane & 7;
               if (row0 + r < M)
-                *reinterpret_cast<float4*>(epi.resid + static_cast<size_t>(row0 + r) * epi.ld_resid + col0 + j * 4) = x4;
+                stg128(epi.resid + static_cast<size_t>(row0 + r) * epi.ld_resid + col0 + j * 4, tv[k]);
             }
             // WAR across proxies: the refill is an async-proxy (TMA) write to a buffer just accessed through the
             // generic proxy → fence, converge, then lane 0 issues the TMA for the chunk two steps ahead.

@@ -89,6 +89,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     }
     cp_async_wait_all();
     __syncthreads();
+    if (q0 + warp * 16 >= T) continue;   // this warp's 16 query rows are all padding (warp-uniform; the block-wide
+                                         // barrier at the top of the next pass is still reached by every warp)
 
     uint32_t qf[KSTEPS][4];
 #pragma unroll

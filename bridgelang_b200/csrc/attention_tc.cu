@@ -430,6 +430,11 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       m = fmaxf(m, xmax[(wg ^ 1) * QT + row]);
       const float ms = m * scale_log2;
       if (warp == 0 && lane == 0) BLB_TRACE(g, 10);
+      // The two groups are deliberately out of phase: group 1 drains the previous tile's O (epilogue: TMEM load,
+      // scale, coalesced stores — no MUFU) while group 0 already runs its exp2 stream, and group 0 does its half of
+      // that epilogue after its exp2s while group 1 is still in MUFU.  The MUFU pipe (the bottleneck of this kernel,
+      // 16 exp2/clk/SM) therefore sees a continuous stream instead of two warps per sub-partition stalling together.
+      if (wg == 1 && g > 0) epilogue(g - 1, sum_prev);
       // P(g-1) must have been consumed by PV(g-1) before it is overwritten
       if (g > 0) mbar_wait(p_empty, static_cast<uint32_t>((g - 1) & 1));
       if (warp == 0 && lane == 0) BLB_TRACE(g, 11);
@@ -472,7 +477,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       if (warp == 0 && lane == 0) BLB_TRACE(g, 12);
       // ---- epilogue of the previous tile (its PV ran underneath this tile's softmax; the other group's partial
       //      sum of tile g-1 was published before this tile's bar.sync) ----
-      if (g > 0) epilogue(g - 1, sum_prev);
+      if (wg == 0 && g > 0) epilogue(g - 1, sum_prev);
       sum_prev = sum;
     }
     if (G > 0) {

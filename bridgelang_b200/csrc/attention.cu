@@ -42,7 +42,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 template <int HD, int HDP>
 __global__ void __launch_bounds__(128, 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H,
-                 float scale_log2, int q_begin) {
+                 float scale_log2, int q_begin, int reverse) {
   constexpr int PITCH = HDP + 8;        // +16 B per row keeps ldmatrix conflict-free
   constexpr int KSTEPS = HDP / 16;
   constexpr int NT_O = HDP / 8;
@@ -54,7 +54,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   __nv_bfloat16* sV = sK + TKP * PITCH;
   __nv_bfloat16* sQ = sV + TKP * PITCH;
 
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int unit = reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int b = unit / H, h = unit % H;
   const int D = H * HD;
   const size_t row_pitch = static_cast<size_t>(3) * D;
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * row_pitch + h * HD;
@@ -200,7 +201,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 
 template <int HD, int HDP>
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int q_begin,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, int reverse) {
   constexpr int PITCH = HDP + 8;
   const int TKP = (T + 63) & ~63;
   const int smem = (2 * TKP + 64) * PITCH * 2;
@@ -214,29 +215,30 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T - q_begin) * T * HD, stream);
-  kern<<<B * H, 128, smem, stream>>>(qkv, out, T, H, scale_log2, q_begin);
+  kern<<<B * H, 128, smem, stream>>>(qkv, out, T, H, scale_log2, q_begin, reverse);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
 }
 
 int attention_tc_first256(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd,
-                          cudaStream_t stream);   // attention_tc.cu
+                          cudaStream_t stream, int reverse);   // attention_tc.cu
 
 static bool g_attn_v1_only = getenv("BLB_ATTN_V1") != nullptr;   // A/B switch: mma.sync kernel for everything
 
-int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream) {
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,
+                   int reverse) {
   if (qkv == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0) return BLB_ERR_ARG;
   if (hd != 64 && hd != 72) return BLB_ERR_SHAPE;
   int q_begin = 0;
   if (!g_attn_v1_only) {
     // tower shapes: the tcgen05 kernel takes query rows [0,256); DINOv2's 5 remaining rows go to the mma.sync kernel
-    const int rc = attention_tc_first256(qkv, out, B, T, H, hd, stream);
+    const int rc = attention_tc_first256(qkv, out, B, T, H, hd, stream, reverse);
     if (rc == 0) q_begin = 256;
     else if (rc != BLB_ERR_SHAPE) return rc;
   }
   if (q_begin >= T) return 0;
-  if (hd == 64) return launch_attention<64, 64>(qkv, out, B, T, H, q_begin, stream);
-  return launch_attention<72, 80>(qkv, out, B, T, H, q_begin, stream);
+  if (hd == 64) return launch_attention<64, 64>(qkv, out, B, T, H, q_begin, stream, reverse);
+  return launch_attention<72, 80>(qkv, out, B, T, H, q_begin, stream, reverse);
 }
 
 }  // namespace blb

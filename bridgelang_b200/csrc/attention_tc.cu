@@ -149,7 +149,7 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 template <int HD, int KX>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out, int B, int T, int H,
-                    float scale_log2, long long* trace) {
+                    float scale_log2, long long* trace, int reverse) {
   // trace (debug only, normally nullptr): CTA 0 records clock64() at pipeline events of tiles [8, 16):
   // trace[(g-8)*16 + e]; e: 0 mma:s_free(g) seen, 1 mma:S(g+1) issued, 2 mma:p_full(g)+o_empty seen, 3 mma:PV(g) issued,
   //   8 sm:s_full seen, 9 sm:S in registers (s_free), 10 sm:max exchanged, 11 sm:p_empty seen, 12 sm:P stored/p_full,
@@ -215,7 +215,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       // ============================== TMA producer (warp-uniform loop, one elected lane issues) ===========
       {
         for (int i = 0; i < my_units; ++i) {
-          const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+          const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+          const int u = reverse ? n_units - 1 - u_i : u_i;
           const int b = u / H, h = u - b * H;
           const int kb = i & 1;                                          // K/V buffer of this unit
           const uint32_t ph = static_cast<uint32_t>(i & 1);              // Q barriers: one use per unit
@@ -340,7 +341,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
 
     auto epilogue = [&](int gp, float own_sum) {
       const int t = gp & 1, i = gp >> 1;
-      const int u = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      const int u = reverse ? n_units - 1 - u_i : u_i;
       const int b = u / H, h = u - b * H;
       const float inv = 1.0f / (own_sum + xsum[(gp & 1) * 2 * QT + (wg ^ 1) * QT + row]);
       mbar_wait(o_full, static_cast<uint32_t>(gp & 1));
@@ -531,7 +533,7 @@ int make_qkv_map(CUtensorMap* map, const void* qkv, int B, int T, int H, int hd,
 long long* g_attn_trace = nullptr;
 
 template <int HD, int KX>
-int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream) {
+int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream, int reverse) {
   using Cfg = AttnCfg<HD, KX>;
   AttnMaps maps;
   int rc = make_qkv_map(&maps.q_main, qkv, B, T, H, HD, 64, QT, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -550,7 +552,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
   const int grid = std::min(num_sms(), B * H);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * 256.0 * T * HD, stream);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, out, B, T, H, scale_log2, g_attn_trace);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, out, B, T, H, scale_log2, g_attn_trace, reverse);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
 }
@@ -562,11 +564,11 @@ void attention_set_trace(long long* device_buffer) { g_attn_trace = device_buffe
 // Handles query rows [0, 256) of every (image, head); returns BLB_ERR_SHAPE when (T, hd) is not one of the two
 // tower configurations this kernel is built for (the caller then uses the mma.sync kernel for everything).
 int attention_tc_first256(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int reverse) {
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return BLB_ERR_ALIGN;
-  if (hd == 64 && T == 256) return launch_tc<64, 0>(qkv, out, B, T, H, stream);
-  if (hd == 64 && T > 256 && T <= 272) return launch_tc<64, 16>(qkv, out, B, T, H, stream);
-  if (hd == 72 && T == 256) return launch_tc<72, 0>(qkv, out, B, T, H, stream);
+  if (hd == 64 && T == 256) return launch_tc<64, 0>(qkv, out, B, T, H, stream, reverse);
+  if (hd == 64 && T > 256 && T <= 272) return launch_tc<64, 16>(qkv, out, B, T, H, stream, reverse);
+  if (hd == 72 && T == 256) return launch_tc<72, 0>(qkv, out, B, T, H, stream, reverse);
   return BLB_ERR_SHAPE;
 }
 

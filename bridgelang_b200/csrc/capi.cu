@@ -4,6 +4,7 @@
 #include "../../include/bridgelang_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "gemm.h"
 
@@ -17,6 +18,7 @@ inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bf
 inline __nv_bfloat16* bf(void* p) { return static_cast<__nv_bfloat16*>(p); }
 
 constexpr int PATCHES = 256;  // 224 / 14 squared
+const bool g_serpentine = getenv("BLB_NO_SERPENTINE") == nullptr;   // A/B switch for the L2-aware row order
 
 struct TowerWs {
   size_t resid, xn, big, total;
@@ -81,32 +83,40 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
   BLB_TRY(write_prefix_tokens(w->prefix, resid, batch, T, w->n_prefix, D, st));
 
   // --- timm Block x n_blocks:  x += ls1(attn(norm1(x)));  x += ls2(mlp(norm2(x))) -----------------------
+  // Every kernel walks its rows in the direction opposite to its producer (serpentine), so it starts on the data the
+  // producer wrote last — still resident in the 126 MB L2 — instead of on data that was evicted long ago.
+  // `dir` = direction in which the residual stream was last written (0 ascending: the patch-embed GEMM).
+  int dir = g_serpentine ? 0 : -1;
   for (int i = 0; i < w->n_blocks; ++i) {
     const blb_block_weights& b = w->blocks_host[i];
     const bool last = i == w->n_blocks - 1;
-    BLB_TRY(layernorm_f32_bf16(resid, D, b.ln1_w, b.ln1_b, xn, D, M, D, w->ln_eps, st));
+    const int r_ln = dir < 0 ? 0 : !dir, r_mm = dir < 0 ? 0 : dir;   // LN/attention/fc2 vs QKV/proj/fc1
+    BLB_TRY(layernorm_f32_bf16(resid, D, b.ln1_w, b.ln1_b, xn, D, M, D, w->ln_eps, st, r_ln));
     {
       GemmEpilogue e;
       e.bias = b.qkv_b;
       e.out = big;
       e.ld_out = 3 * D;
+      e.reverse = r_mm;
       BLB_TRY(gemm_bf16(xn, D, bf(b.qkv_w), D, M, 3 * D, D, EPI_BIAS, e, st));
     }
-    BLB_TRY(attention_bf16(big, xn, batch, T, w->heads, w->head_dim, st));
+    BLB_TRY(attention_bf16(big, xn, batch, T, w->heads, w->head_dim, st, r_ln));
     {
       GemmEpilogue e;
       e.bias = b.proj_b;
       e.gamma = b.ls1;
       e.resid = resid;
       e.ld_resid = D;
+      e.reverse = r_mm;
       BLB_TRY(gemm_bf16(xn, D, bf(b.proj_w), D, M, D, D, EPI_RESIDUAL, e, st));
     }
-    BLB_TRY(layernorm_f32_bf16(resid, D, b.ln2_w, b.ln2_b, xn, D, M, D, w->ln_eps, st));
+    BLB_TRY(layernorm_f32_bf16(resid, D, b.ln2_w, b.ln2_b, xn, D, M, D, w->ln_eps, st, r_ln));
     {
       GemmEpilogue e;
       e.bias = b.fc1_b;
       e.out = big;
       e.ld_out = Hm;
+      e.reverse = r_mm;
       BLB_TRY(gemm_bf16(xn, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
     }
     {
@@ -125,8 +135,10 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
         e.tok_out = PATCHES;
         e.tok_shift = -w->n_prefix;
       }
+      e.reverse = r_ln;
       BLB_TRY(gemm_bf16(big, Hm, bf(b.fc2_w), Hm, M, D, Hm, EPI_RESIDUAL, e, st));
     }
+    if (dir >= 0) dir = r_ln;   // fc2 wrote the residual stream in direction r_ln
   }
   return 0;
 }
@@ -153,6 +165,7 @@ int projector_forward(const blb_projector_weights* w, const void* x, int ldx, in
   e2.bias = w->fc2_b;
   e2.out = h2;
   e2.ld_out = w->out_dim;
+  e2.reverse = g_serpentine ? 1 : 0;   // start on the rows of h1 that fc1 wrote last (still in L2)
   BLB_TRY(gemm_bf16(h1, w->hidden_dim, bf(w->fc2_w), w->hidden_dim, rows, w->out_dim, w->hidden_dim, EPI_BIAS_GELU, e2,
                     st));
   GemmEpilogue e3;

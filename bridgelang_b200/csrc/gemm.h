@@ -31,6 +31,9 @@ struct GemmEpilogue {
   int tok_in = 0;                 // 0 → identity
   int tok_out = 0;
   int tok_shift = 0;
+  // walk the tiles last-to-first: a kernel that starts where its producer finished finds that data still in the
+  // 126 MB L2 (the schedule in capi.cu alternates directions along the producer → consumer chain)
+  int reverse = 0;
 };
 
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, int mode,
@@ -58,10 +61,11 @@ void count_launch(int n);
 
 // layernorm.cu — timm LayerNorm(eps) over the last dim of an fp32 [rows, D] stream → bf16
 int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y, int ldy, int rows,
-                       int D, float eps, cudaStream_t stream);
+                       int D, float eps, cudaStream_t stream, int reverse = 0);
 
 // attention.cu — softmax(q kᵀ · hd^-0.5) v over packed qkv [B*T, 3*H*hd] → out [B*T, H*hd]
-int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream);
+int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,
+                   int reverse = 0);
 
 // attention_tc.cu debug hook: CTA 0 writes clock64() stamps of pipeline events into this device buffer (or nullptr)
 void attention_set_trace(long long* device_buffer);

@@ -131,7 +131,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // whole warp walks the (warp-uniform) loop; one elected lane issues
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    for (int tile_i = first_tile; tile_i < num_tiles; tile_i += tile_step) {
+      const int tile = epi.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
       const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
@@ -211,8 +212,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* rbar = rld_bar + ew * 2;
     auto issue_resid = [&](int sq) {
       const int lt = sq / CHUNKS, c = sq - lt * CHUNKS;
-      const int tl = first_tile + lt * tile_step;
-      if (tl >= num_tiles) return;
+      const int tl_i = first_tile + lt * tile_step;
+      if (tl_i >= num_tiles) return;
+      const int tl = epi.reverse ? num_tiles - 1 - tl_i : tl_i;
       const int mb = tl / n_tiles, nb = tl - mb * n_tiles;
       const int r0 = mb * tile_m + static_cast<int>(cta_rank) * BM + quarter * 32;
       const int c0 = nb * BN + half * COLS_PER_WARP + c * 32;
@@ -224,7 +226,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       issue_resid(0);
       issue_resid(1);
     }
-    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    for (int tile_i = first_tile; tile_i < num_tiles; tile_i += tile_step) {
+      const int tile = epi.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int m_blk = tile / n_tiles;
       const int n_blk = tile - m_blk * n_tiles;
       const int row = m_blk * tile_m + static_cast<int>(cta_rank) * BM + quarter * 32 + lane;

@@ -61,6 +61,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * row_pitch + h * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  pdl_launch_dependents();
+  pdl_wait();
 
   // ---- stage K and V of this (image, head) once -------------------------------------------------
   for (int i = threadIdx.x; i < TKP * CHUNKS; i += blockDim.x) {
@@ -215,7 +217,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T - q_begin) * T * HD, stream);
-  kern<<<B * H, 128, smem, stream>>>(qkv, out, T, H, scale_log2, q_begin, reverse);
+  cudaError_t le = launch_pdl(kern, dim3(B * H), dim3(128), smem, stream, qkv, out, T, H, scale_log2, q_begin, reverse);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
 }

@@ -204,6 +204,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // PDL: the prologue above overlapped with the QKV GEMM's tail
+  pdl_wait();
 
   uint8_t* sQ[2] = {smem + Cfg::OFF_Q0, smem + Cfg::OFF_Q1};
   uint8_t* sK[2] = {smem + Cfg::OFF_K, smem + Cfg::OFF_K + Cfg::KV_BYTES};
@@ -552,7 +554,9 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
   const int grid = std::min(num_sms(), B * H);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * 256.0 * T * HD, stream);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps, out, B, T, H, scale_log2, g_attn_trace, reverse);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, maps, out, B, T, H,
+                              scale_log2, g_attn_trace, reverse);
+  if (le != cudaSuccess) return static_cast<int>(le);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
 }

@@ -41,6 +41,24 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
 void gemm_set_cta_group(int ctas);
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int num_sms();
+bool pdl_enabled();   // launch kernels with cudaLaunchAttributeProgrammaticStreamSerialization (default on)
+
+// <<<>>> replacement that adds the PDL attribute; the kernel must call pdl_wait() before touching global data
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // Optional per-launch device timing (bench.py's roofline): when enabled, every kernel launch is bracketed by a
 // pair of CUDA events on its own stream; timing_collect() sums them per category after the caller synchronised.

@@ -125,6 +125,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (CTAS == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above overlapped with the previous kernel's tail; from here on we read its output
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == W_TMA) {
     // ===================================== TMA producer ==========================================
@@ -456,6 +459,10 @@ static bool g_resid_direct = getenv("BLB_RESID_DIRECT") != nullptr;   // A/B swi
 static long long g_launches = 0;
 
 void gemm_set_cta_group(int ctas) { g_force_ctas = ctas; }
+bool pdl_enabled() {
+  static const bool on = getenv("BLB_NO_PDL") == nullptr;
+  return on;
+}
 
 // ---- optional per-launch timing ------------------------------------------------------------------
 namespace {
@@ -529,13 +536,15 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   TimingScope ts(TIME_GEMM, 2.0 * M * N * K, stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, M, N, K, epi);
   count_launch(1);

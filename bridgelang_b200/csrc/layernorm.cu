@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk = reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
   const int row = blk * 8 + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   constexpr int D = VEC * 128;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
@@ -57,10 +59,11 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
   if (x == nullptr || w == nullptr || b == nullptr || y == nullptr || rows <= 0) return BLB_ERR_ARG;
   if (D % 128 != 0 || D > 2048 || ldx % 4 != 0 || ldy % 4 != 0) return BLB_ERR_SHAPE;
   const dim3 grid((rows + 7) / 8), block(256);
+  cudaError_t le = cudaSuccess;
   TimingScope ts(TIME_LAYERNORM, 6.0 * rows * D, stream);   // bytes: fp32 read + bf16 write
   switch (D / 128) {
 #define BLB_LN_CASE(V) \
-  case V: layernorm_kernel<V><<<grid, block, 0, stream>>>(x, ldx, w, b, y, ldy, rows, eps, reverse); break;
+  case V: le = launch_pdl(layernorm_kernel<V>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, eps, reverse); break;
     BLB_LN_CASE(1) BLB_LN_CASE(2) BLB_LN_CASE(3) BLB_LN_CASE(4) BLB_LN_CASE(5) BLB_LN_CASE(6) BLB_LN_CASE(7)
     BLB_LN_CASE(8) BLB_LN_CASE(9) BLB_LN_CASE(10) BLB_LN_CASE(11) BLB_LN_CASE(12) BLB_LN_CASE(13)
     BLB_LN_CASE(14) BLB_LN_CASE(15) BLB_LN_CASE(16)
@@ -68,6 +71,7 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
     default: return BLB_ERR_SHAPE;
   }
   count_launch(1);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
 

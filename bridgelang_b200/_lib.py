@@ -24,13 +24,15 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p), ("gamma", C.c_void_p), ("resid", C.c_void_p), ("ld_resid", C.c_int32),
         ("out", C.c_void_p), ("ld_out", C.c_int32), ("out_col_off", C.c_int32), ("pos", C.c_void_p),
         ("tok_in", C.c_int32), ("tok_out", C.c_int32), ("tok_shift", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
+        ("stats_out", C.c_void_p), ("xb_out", C.c_void_p), ("ld_xb", C.c_int32),
     ]
 
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1",
-        "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+        "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2", "qkv_colsum", "fc1_colsum")]
 
 
 class VitWeights(C.Structure):
@@ -38,7 +40,7 @@ class VitWeights(C.Structure):
         ("dim", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32), ("hidden_pad", C.c_int32),
         ("n_prefix", C.c_int32), ("n_blocks", C.c_int32), ("patch_ldk", C.c_int32), ("ln_eps", C.c_float),
         ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("pos_embed", C.c_void_p), ("prefix", C.c_void_p),
-        ("blocks_host", C.POINTER(BlockWeights)),
+        ("blocks_host", C.POINTER(BlockWeights)), ("ln_folded", C.c_int32),
     ]
 
 
@@ -60,8 +62,13 @@ _SIGNATURES = {
     "blb_timing_enable": (None, [C.c_int]),
     "blb_timing_reset": (None, []),
     "blb_timing_collect": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "blb_timing_records": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]),
     "blb_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(Epilogue), C.c_void_p]),
+    "blb_gemm_stats_parts": (C.c_int, [C.c_int]),
+    "blb_rowstats_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]),
     "blb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_float, C.c_void_p]),
     "blb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

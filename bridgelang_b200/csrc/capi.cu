@@ -21,11 +21,13 @@ constexpr int PATCHES = 256;  // 224 / 14 squared
 const bool g_serpentine = getenv("BLB_NO_SERPENTINE") == nullptr;   // A/B switch for the L2-aware row order
 
 struct TowerWs {
-  size_t resid, xn, big, total;
+  size_t resid, xn, big, xb, stats, total;
 };
 
 // resid fp32 [M,D] | xn bf16 [M,D] (LayerNorm out, then attention out) | big bf16 [M, max(3D, Hm_pad)]
 // (im2col staging, then packed qkv, then the MLP hidden — lifetimes never overlap)
+// LN-folded towers add: xb bf16 [M,D] (bf16 copy of the residual stream = A operand of qkv / fc1) and
+// stats float2 [M, parts] (per-row partial sums written by the proj / fc2 epilogues)
 TowerWs tower_ws(const blb_vit_weights* w, int batch) {
   const size_t T = PATCHES + w->n_prefix, M = static_cast<size_t>(batch) * T, D = w->dim;
   const size_t wide = std::max<size_t>(std::max<size_t>(3 * D, w->hidden_pad), w->patch_ldk);
@@ -33,7 +35,9 @@ TowerWs tower_ws(const blb_vit_weights* w, int batch) {
   s.resid = 0;
   s.xn = align_up(M * D * 4);
   s.big = s.xn + align_up(M * D * 2);
-  s.total = s.big + align_up(M * wide * 2);
+  s.xb = s.big + align_up(M * wide * 2);
+  s.stats = s.xb + (w->ln_folded ? align_up(M * D * 2) : 0);
+  s.total = s.stats + (w->ln_folded ? align_up(M * static_cast<size_t>(gemm_stats_parts(w->dim)) * 8) : 0);
   return s;
 }
 
@@ -53,6 +57,88 @@ int check_vit(const blb_vit_weights* w) {
     int _rc = (expr);        \
     if (_rc != 0) return _rc; \
   } while (0)
+
+// timm Block x n_blocks with norm1 / norm2 folded away: per block
+//   qkv  GEMM  A = xb (bf16 copy of x), W' = W·diag(ln1_w), epilogue rstd·(acc − mean·colsum) + (b + W·ln1_b)
+//   attention
+//   proj GEMM  x += ls1·(acc + b);   epilogue also writes xb and the per-row partial (sum, sumsq) of the new x
+//   fc1  GEMM  A = xb, folded like qkv, + GELU
+//   fc2  GEMM  x += ls2·(acc + b);   writes xb + stats for the next block (or the concat slice when last)
+// 5 launches per block instead of 7; the residual stream is read once and written once per branch.
+int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int ld_out, int out_col_off, float* resid,
+                           __nv_bfloat16* attn, __nv_bfloat16* big, __nv_bfloat16* xb, float2* stats,
+                           cudaStream_t st) {
+  const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
+  const int parts = gemm_stats_parts(D);
+  if (parts <= 0) return BLB_ERR_SHAPE;
+  BLB_TRY(rowstats_cast_f32_bf16(resid, D, xb, D, stats, parts, M, D, st));
+  int rev = 0;   // serpentine: every kernel walks its rows opposite to its producer (see tower_forward)
+  auto next_dir = [&]() { if (g_serpentine) rev ^= 1; return rev; };
+  for (int i = 0; i < w->n_blocks; ++i) {
+    const blb_block_weights& b = w->blocks_host[i];
+    if (b.qkv_colsum == nullptr || b.fc1_colsum == nullptr) return BLB_ERR_ARG;
+    const bool last = i == w->n_blocks - 1;
+    {
+      GemmEpilogue e;
+      e.bias = b.qkv_b;
+      e.out = big;
+      e.ld_out = 3 * D;
+      e.ln_stats = stats;
+      e.ln_colsum = b.qkv_colsum;
+      e.ln_parts = parts;
+      e.ln_eps = w->ln_eps;
+      e.reverse = next_dir();
+      BLB_TRY(gemm_bf16(xb, D, bf(b.qkv_w), D, M, 3 * D, D, EPI_BIAS, e, st));
+    }
+    BLB_TRY(attention_bf16(big, attn, batch, T, w->heads, w->head_dim, st, next_dir()));
+    {
+      GemmEpilogue e;
+      e.bias = b.proj_b;
+      e.gamma = b.ls1;
+      e.resid = resid;
+      e.ld_resid = D;
+      e.stats_out = stats;
+      e.xb_out = xb;
+      e.ld_xb = D;
+      e.reverse = next_dir();
+      BLB_TRY(gemm_bf16(attn, D, bf(b.proj_w), D, M, D, D, EPI_RESIDUAL, e, st));
+    }
+    {
+      GemmEpilogue e;
+      e.bias = b.fc1_b;
+      e.out = big;
+      e.ld_out = Hm;
+      e.ln_stats = stats;
+      e.ln_colsum = b.fc1_colsum;
+      e.ln_parts = parts;
+      e.ln_eps = w->ln_eps;
+      e.reverse = next_dir();
+      BLB_TRY(gemm_bf16(xb, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
+    }
+    {
+      GemmEpilogue e;
+      e.bias = b.fc2_b;
+      e.gamma = b.ls2;
+      e.resid = resid;
+      e.ld_resid = D;
+      if (last) {   // concat write, as in tower_forward
+        e.out = bf(out);
+        e.ld_out = ld_out;
+        e.out_col_off = out_col_off;
+        e.tok_in = T;
+        e.tok_out = PATCHES;
+        e.tok_shift = -w->n_prefix;
+      } else {
+        e.stats_out = stats;
+        e.xb_out = xb;
+        e.ld_xb = D;
+      }
+      e.reverse = next_dir();
+      BLB_TRY(gemm_bf16(big, Hm, bf(b.fc2_w), Hm, M, D, Hm, EPI_RESIDUAL, e, st));
+    }
+  }
+  return 0;
+}
 
 int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void* out, int ld_out, int out_col_off,
                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -81,6 +167,10 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
                       st));
   }
   BLB_TRY(write_prefix_tokens(w->prefix, resid, batch, T, w->n_prefix, D, st));
+  if (w->ln_folded)
+    return tower_blocks_ln_folded(w, batch, out, ld_out, out_col_off, resid, xn, big,
+                                  reinterpret_cast<__nv_bfloat16*>(base + ws.xb),
+                                  reinterpret_cast<float2*>(base + ws.stats), st);
 
   // --- timm Block x n_blocks:  x += ls1(attn(norm1(x)));  x += ls2(mlp(norm2(x))) -----------------------
   // Every kernel walks its rows in the direction opposite to its producer (serpentine), so it starts on the data the
@@ -184,7 +274,7 @@ int projector_forward(const blb_projector_weights* w, const void* x, int ldx, in
 #pragma GCC visibility push(default)
 extern "C" {
 
-int blb_abi_version(void) { return 1; }
+int blb_abi_version(void) { return 2; }
 
 const char* blb_status_string(int status) {
   switch (status) {
@@ -209,6 +299,11 @@ int blb_timing_collect(int category, double* ms, double* work, long long* launch
   return timing_collect(category, ms, work, launches);
 }
 
+int blb_timing_records(int max_records, int* category, long long* tag, double* ms, double* work) {
+  if (max_records <= 0 || category == nullptr || tag == nullptr || ms == nullptr || work == nullptr) return BLB_ERR_ARG;
+  return timing_records(max_records, category, tag, ms, work);
+}
+
 int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int mode,
                   const blb_epilogue* epi, void* stream) {
   if (epi == nullptr) return BLB_ERR_ARG;
@@ -224,6 +319,14 @@ int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
   e.tok_in = epi->tok_in;
   e.tok_out = epi->tok_out;
   e.tok_shift = epi->tok_shift;
+  e.ln_stats = reinterpret_cast<const float2*>(epi->ln_stats);
+  e.ln_colsum = epi->ln_colsum;
+  e.ln_parts = epi->ln_parts;
+  e.ln_eps = epi->ln_eps;
+  e.stats_out = reinterpret_cast<float2*>(epi->stats_out);
+  e.xb_out = bf(epi->xb_out);
+  e.ld_xb = epi->ld_xb;
+  if (e.xb_out != nullptr && e.ld_xb % 8 != 0) return BLB_ERR_ARG;
   if (mode == EPI_BIAS || mode == EPI_BIAS_GELU) {
     if (e.out == nullptr || e.ld_out % 8 != 0 || e.out_col_off % 8 != 0) return BLB_ERR_ARG;
   } else if (mode == EPI_RESIDUAL) {
@@ -235,6 +338,14 @@ int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
     return BLB_ERR_ARG;
   }
   return gemm_bf16(bf(A), lda, bf(W), ldw, M, N, K, mode, e, as_stream(stream));
+}
+
+int blb_gemm_stats_parts(int N) { return N > 0 ? gemm_stats_parts(N) : 0; }
+
+int blb_rowstats_cast(const float* x, int ldx, void* y, int ldy, float* stats, int parts, int rows, int D,
+                      void* stream) {
+  return rowstats_cast_f32_bf16(x, ldx, bf(y), ldy, reinterpret_cast<float2*>(stats), parts, rows, D,
+                                as_stream(stream));
 }
 
 int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void* y, int ldy, int rows, int D,

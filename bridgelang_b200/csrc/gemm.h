@@ -34,11 +34,25 @@ struct GemmEpilogue {
   // walk the tiles last-to-first: a kernel that starts where its producer finished finds that data still in the
   // 126 MB L2 (the schedule in capi.cu alternates directions along the producer → consumer chain)
   int reverse = 0;
+  // ---- LayerNorm folded into the neighbouring GEMMs -----------------------------------------
+  // consumer (EPI_BIAS / EPI_BIAS_GELU): A is the bf16 copy of the UN-normalised fp32 rows, W is the LN-weight-folded
+  // bf16 matrix W' = W·diag(ln_w), bias is b + W·ln_b, and  out = rstd_m·(acc − mean_m·colsum_n) + bias_n
+  // with (mean, rstd) of row m rebuilt from `ln_parts` partial (sum, sum of squares) pairs written by the producer.
+  const float2* ln_stats = nullptr;   // [ln_parts, M]
+  const float* ln_colsum = nullptr;   // [N]  Σ_k W'[n,k] (of the bf16-rounded values, in fp32)
+  int ln_parts = 0;
+  float ln_eps = 0.f;
+  // producer (EPI_RESIDUAL): per-row partial statistics of the new fp32 rows, one pair per epilogue warp column
+  // span → [gemm_stats_parts(N), M], and the bf16 copy of the new rows that the consumer uses as its A operand
+  float2* stats_out = nullptr;
+  __nv_bfloat16* xb_out = nullptr;
+  int ld_xb = 0;
 };
 
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, int mode,
               const GemmEpilogue& epi, cudaStream_t stream);
 void gemm_set_cta_group(int ctas);
+int gemm_stats_parts(int N);   // number of (sum, sumsq) pairs per row an EPI_RESIDUAL launch with this N writes
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int num_sms();
 bool pdl_enabled();   // launch kernels with cudaLaunchAttributeProgrammaticStreamSerialization (default on)
@@ -66,13 +80,15 @@ enum TimingCategory : int { TIME_GEMM = 0, TIME_ATTENTION = 1, TIME_LAYERNORM = 
 void timing_enable(int on);
 bool timing_enabled();
 void timing_begin(cudaStream_t s);
-void timing_end(int cat, double work, cudaStream_t s);
+void timing_end(int cat, double work, cudaStream_t s, long long tag);
+int timing_records(int max_records, int* cat, long long* tag, double* ms, double* work);
 int timing_collect(int cat, double* ms, double* work, long long* launches);
 void timing_reset();
 struct TimingScope {
-  int cat; double work; cudaStream_t s; bool on;
-  TimingScope(int c, double w, cudaStream_t st) : cat(c), work(w), s(st), on(timing_enabled()) { if (on) timing_begin(s); }
-  ~TimingScope() { if (on) timing_end(cat, work, s); }
+  int cat; double work; cudaStream_t s; bool on; long long tag;
+  TimingScope(int c, double w, cudaStream_t st, long long tg = 0)
+      : cat(c), work(w), s(st), on(timing_enabled()), tag(tg) { if (on) timing_begin(s); }
+  ~TimingScope() { if (on) timing_end(cat, work, s, tag); }
 };
 long long launch_count();
 void count_launch(int n);
@@ -80,6 +96,11 @@ void count_launch(int n);
 // layernorm.cu — timm LayerNorm(eps) over the last dim of an fp32 [rows, D] stream → bf16
 int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y, int ldy, int rows,
                        int D, float eps, cudaStream_t stream, int reverse = 0);
+
+// fp32 rows → bf16 copy + full-row (sum, sumsq) in part 0 of `parts` (others zero): primes the LN-folded chain after
+// the patch-embed stage (the later blocks get both from the EPI_RESIDUAL epilogues)
+int rowstats_cast_f32_bf16(const float* x, int ldx, __nv_bfloat16* y, int ldy, float2* stats, int parts, int rows,
+                           int D, cudaStream_t stream);
 
 // attention.cu — softmax(q kᵀ · hd^-0.5) v over packed qkv [B*T, 3*H*hd] → out [B*T, H*hd]
 int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,

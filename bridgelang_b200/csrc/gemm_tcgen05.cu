@@ -34,6 +34,7 @@ constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int RCHUNK_BYTES = 32 * 32 * 4;   // one epilogue warp's [32 rows x 32 cols] fp32 residual chunk
 
 constexpr int OCHUNK_BYTES = 32 * 32 * 2;   // one epilogue warp's [32 rows x 32 cols] bf16 output staging chunk
+constexpr int VEC_BYTES = 2 * 128 * 4;      // one epilogue warp's per-tile copy of two per-column fp32 vectors (<= 128 cols)
 
 template <int BN, int CTAS, bool RTMA = false, bool OBUF = false>
 struct GemmCfg {
@@ -44,7 +45,10 @@ struct GemmCfg {
   // RTMA: every epilogue warp owns two TMA-fed residual chunk buffers (prefetched two chunks ahead)
   // OBUF: every epilogue warp owns one bf16 staging chunk used to transpose its row-per-lane results into
   //       row-contiguous (coalesced) global stores
-  static constexpr int EPI_BYTES = RTMA ? NUM_EPI_WARPS * 2 * RCHUNK_BYTES : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : 0);
+  // every epilogue warp also keeps this tile's slice of bias and of gamma / LN column sums in smem (VEC_BYTES): one
+  // coalesced load per tile, issued before the accumulator is ready, instead of 8-16 dependent LDGs per 32-column chunk
+  static constexpr int STAGE_EPI_BYTES = RTMA ? NUM_EPI_WARPS * 2 * RCHUNK_BYTES : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : 0);
+  static constexpr int EPI_BYTES = STAGE_EPI_BYTES + NUM_EPI_WARPS * VEC_BYTES;
   static constexpr int STAGES = (200 * 1024 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 512;                    // 2 accumulator stages of BN (<=256) columns
   static constexpr int ACC_STRIDE = 256;
@@ -211,6 +215,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     // RTMA: flat sequence seq = local_tile * CHUNKS + chunk; residual chunk `seq` lands in buffer seq & 1 of this
     // warp, its TMA is issued two sequence steps ahead (i.e. possibly already for the next tile).
+    const uint32_t vec_s = smem_u32(smem_r) + Cfg::STAGE_EPI_BYTES + ew * VEC_BYTES;
     uint8_t* rbuf = smem_r + ew * 2 * RCHUNK_BYTES;
     uint64_t* rbar = rld_bar + ew * 2;
     auto issue_resid = [&](int sq) {
@@ -254,6 +259,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       const uint32_t obuf_s = smem_u32(smem_r) + ew * OCHUNK_BYTES;
 
+      // folded LayerNorm, consumer side: rebuild (mean, rstd) of this lane's row from the producer's partial sums
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if constexpr (OBUF) {
+        if (epi.ln_stats != nullptr && row_ok) {
+          // stats are [part][row]: a warp reads 32 consecutive pairs per part; four independent loads in flight so the
+          // whole rebuild costs ~one L2 round trip (it sits in front of every tile's epilogue)
+          const float2* sp = epi.ln_stats + row;
+          float s1 = 0.f, s2 = 0.f;
+          for (int p0 = 0; p0 < epi.ln_parts; p0 += 4) {
+            float2 t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              t[q] = p0 + q < epi.ln_parts ? __ldg(sp + static_cast<size_t>(p0 + q) * M) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              s1 += t[q].x;
+              s2 += t[q].y;
+            }
+          }
+          const float inv_k = 1.0f / static_cast<float>(K);
+          ln_mean = s1 * inv_k;
+          ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + epi.ln_eps);
+        }
+      }
+      float part_sum = 0.f, part_sq = 0.f;   // producer side: this lane's row over this warp's column span
+
+      // this warp's COLS_PER_WARP-wide slices of bias (vec 0) and of gamma | LN column sums (vec 1) → smem
+      {
+        const int cw0 = n_blk * BN + half * COLS_PER_WARP;
+        const float* v1 = MODE == EPI_RESIDUAL ? epi.gamma : (OBUF && epi.ln_stats != nullptr ? epi.ln_colsum : nullptr);
+        const float fill1 = MODE == EPI_RESIDUAL ? 1.f : 0.f;
+        if (lane < COLS_PER_WARP / 4) {
+          const float4 a4 = epi.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(epi.bias + cw0) + lane)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 g4 = v1 != nullptr ? __ldg(reinterpret_cast<const float4*>(v1 + cw0) + lane)
+                                          : make_float4(fill1, fill1, fill1, fill1);
+          sts128(vec_s + lane * 16, make_uint4(__float_as_uint(a4.x), __float_as_uint(a4.y), __float_as_uint(a4.z),
+                                               __float_as_uint(a4.w)));
+          sts128(vec_s + 512 + lane * 16, make_uint4(__float_as_uint(g4.x), __float_as_uint(g4.y),
+                                                     __float_as_uint(g4.z), __float_as_uint(g4.w)));
+        }
+        __syncwarp();
+      }
+
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -280,12 +329,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (epi.bias != nullptr) {
+        if constexpr (OBUF) {
+          if (epi.ln_stats != nullptr) {   // LN(x)·Wᵀ = rstd·(x·W'ᵀ − mean·colsum(W'))  (+ folded bias below)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            for (int j = 0; j < 32; j += 4) {
+              const uint4 c4 = lds128(vec_s + 512 + (c * 32 + j) * 4);
+              v[j] = (v[j] - ln_mean * __uint_as_float(c4.x)) * ln_rstd;
+              v[j + 1] = (v[j + 1] - ln_mean * __uint_as_float(c4.y)) * ln_rstd;
+              v[j + 2] = (v[j + 2] - ln_mean * __uint_as_float(c4.z)) * ln_rstd;
+              v[j + 3] = (v[j + 3] - ln_mean * __uint_as_float(c4.w)) * ln_rstd;
+            }
           }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {   // + bias (zeros when there is none)
+          const uint4 b4 = lds128(vec_s + (c * 32 + j) * 4);
+          v[j] += __uint_as_float(b4.x); v[j + 1] += __uint_as_float(b4.y);
+          v[j + 2] += __uint_as_float(b4.z); v[j + 3] += __uint_as_float(b4.w);
         }
         if constexpr (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU) {
           if constexpr (MODE == EPI_BIAS_GELU) {
@@ -330,12 +390,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         } else {  // EPI_RESIDUAL:  x += gamma * (acc + bias)   (timm Block: x + ls(branch(x)))
           if (row_ok) {
             float* x = epi.resid + static_cast<size_t>(row) * epi.ld_resid + col0;
-            if (epi.gamma != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(epi.gamma + col0 + j));
-                v[j] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
-              }
+            for (int j = 0; j < 32; j += 4) {   // LayerScale gamma (ones when there is none)
+              const uint4 g4 = lds128(vec_s + 512 + (c * 32 + j) * 4);
+              v[j] *= __uint_as_float(g4.x); v[j + 1] *= __uint_as_float(g4.y);
+              v[j + 2] *= __uint_as_float(g4.z); v[j + 3] *= __uint_as_float(g4.w);
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -345,6 +404,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               x4.x += v[j]; x4.y += v[j + 1]; x4.z += v[j + 2]; x4.w += v[j + 3];
               v[j] = x4.x; v[j + 1] = x4.y; v[j + 2] = x4.z; v[j + 3] = x4.w;
               if constexpr (!RTMA) *reinterpret_cast<float4*>(x + j) = x4;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              part_sum += v[j];
+              part_sq = fmaf(v[j], v[j], part_sq);
+            }
+            if constexpr (!RTMA) {
+              if (epi.xb_out != nullptr) {
+                __nv_bfloat16* o = epi.xb_out + static_cast<size_t>(row) * epi.ld_xb + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  pk.x = pack_bf16x2(v[j], v[j + 1]);
+                  pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                  pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(o + j) = pk;
+                }
+              }
             }
             if (epi.out != nullptr && dst_ok) {
               __nv_bfloat16* o = epi.out + static_cast<size_t>(dst_row) * epi.ld_out + epi.out_col_off + col0;
@@ -381,6 +459,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               if (row0 + r < M)
                 stg128(epi.resid + static_cast<size_t>(row0 + r) * epi.ld_resid + col0 + j * 4, tv[k]);
             }
+            if (epi.xb_out != nullptr) {   // bf16 copy for the LN-folded consumer: 4 rows x 64 contiguous bytes per store
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int r = k * 4 + (lane >> 3), j = lane & 7;
+                if (row0 + r < M) {
+                  uint2 pk;
+                  pk.x = pack_bf16x2(__uint_as_float(tv[k].x), __uint_as_float(tv[k].y));
+                  pk.y = pack_bf16x2(__uint_as_float(tv[k].z), __uint_as_float(tv[k].w));
+                  *reinterpret_cast<uint2*>(epi.xb_out + static_cast<size_t>(row0 + r) * epi.ld_xb + col0 + j * 4) = pk;
+                }
+              }
+            }
             // WAR across proxies: the refill is an async-proxy (TMA) write to a buffer just accessed through the
             // generic proxy → fence, converge, then lane 0 issues the TMA for the chunk two steps ahead.
             fence_proxy_async_smem();
@@ -389,6 +479,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ++seq;
           }
         }
+      }
+      if constexpr (MODE == EPI_RESIDUAL) {
+        if (epi.stats_out != nullptr && row_ok)
+          epi.stats_out[static_cast<size_t>(2 * n_blk + half) * M + row] = make_float2(part_sum, part_sq);
       }
       // all TMEM reads of this accumulator stage are complete → hand it back to the MMA warp
       tc_fence_before();
@@ -459,6 +553,11 @@ static bool g_resid_direct = getenv("BLB_RESID_DIRECT") != nullptr;   // A/B swi
 static long long g_launches = 0;
 
 void gemm_set_cta_group(int ctas) { g_force_ctas = ctas; }
+static int pick_bn(int N) { return N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 0; }
+int gemm_stats_parts(int N) {
+  const int bn = pick_bn(N);
+  return bn == 0 ? 0 : 2 * (N / bn);
+}
 bool pdl_enabled() {
   static const bool on = getenv("BLB_NO_PDL") == nullptr;
   return on;
@@ -466,7 +565,7 @@ bool pdl_enabled() {
 
 // ---- optional per-launch timing ------------------------------------------------------------------
 namespace {
-struct TimingRec { int cat; double work; cudaEvent_t e0, e1; };
+struct TimingRec { int cat; long long tag; double work; cudaEvent_t e0, e1; };
 bool g_timing = false;
 std::vector<TimingRec> g_recs;
 std::vector<cudaEvent_t> g_event_pool;
@@ -479,10 +578,10 @@ cudaEvent_t get_event() {
 void timing_enable(int on) { g_timing = on != 0; }
 bool timing_enabled() { return g_timing; }
 void timing_begin(cudaStream_t s) { g_pending_e0 = get_event(); cudaEventRecord(g_pending_e0, s); }
-void timing_end(int cat, double work, cudaStream_t s) {
+void timing_end(int cat, double work, cudaStream_t s, long long tag) {
   cudaEvent_t e1 = get_event();
   cudaEventRecord(e1, s);
-  g_recs.push_back({cat, work, g_pending_e0, e1});
+  g_recs.push_back({cat, tag, work, g_pending_e0, e1});
   g_pending_e0 = nullptr;
 }
 void timing_reset() {
@@ -502,6 +601,18 @@ int timing_collect(int cat, double* ms, double* work, long long* launches) {
   if (work) *work = w;
   if (launches) *launches = n;
   return 0;
+}
+int timing_records(int max_records, int* cat, long long* tag, double* ms, double* work) {
+  int n = 0;
+  for (auto& r : g_recs) {
+    if (n >= max_records) break;
+    float f = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&f, r.e0, r.e1);
+    if (e != cudaSuccess) return -static_cast<int>(e);
+    cat[n] = r.cat; tag[n] = r.tag; ms[n] = f; work[n] = r.work;
+    ++n;
+  }
+  return n;
 }
 long long launch_count() { return g_launches; }
 void count_launch(int n) { g_launches += n; }
@@ -545,7 +656,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  TimingScope ts(TIME_GEMM, 2.0 * M * N * K, stream);
+  // tag: epilogue mode | LN-folded consumer | stats/xb producer | N | K  (blb_timing_records)
+  const long long tag = (static_cast<long long>(MODE) << 44) | (static_cast<long long>(epi.ln_stats != nullptr) << 43) |
+                        (static_cast<long long>(epi.xb_out != nullptr) << 42) | (static_cast<long long>(N) << 20) | K;
+  TimingScope ts(TIME_GEMM, 2.0 * M * N * K, stream, tag);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, M, N, K, epi);
   count_launch(1);
   return static_cast<int>(e);
@@ -574,11 +688,10 @@ static int launch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, i
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, int mode,
               const GemmEpilogue& epi, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || A == nullptr || W == nullptr) return BLB_ERR_ARG;
-  int bn = 0;
-  if (N % 256 == 0) bn = 256;
-  else if (N % 192 == 0) bn = 192;
-  else if (N % 128 == 0) bn = 128;
-  else return BLB_ERR_SHAPE;
+  const int bn = pick_bn(N);
+  if (bn == 0) return BLB_ERR_SHAPE;
+  if (epi.ln_stats != nullptr && (epi.ln_colsum == nullptr || epi.ln_parts <= 0 || mode > EPI_BIAS_GELU)) return BLB_ERR_ARG;
+  if ((epi.stats_out != nullptr || epi.xb_out != nullptr) && mode != EPI_RESIDUAL) return BLB_ERR_ARG;
   const int ctas = g_force_ctas != 0 ? g_force_ctas : 2;
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);

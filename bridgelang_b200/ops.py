@@ -48,9 +48,14 @@ def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, resid=None, out=None,
-         out_col_off: int = 0, pos=None, tok_in: int = 0, tok_out: int = 0, tok_shift: int = 0) -> Optional[torch.Tensor]:
-    """C = a[M,K] @ w[N,K]^T with the fused epilogue `mode` (see include/bridgelang_b200.h)."""
-    _need_cuda(a, w, bias, gamma, resid, out, pos)
+         out_col_off: int = 0, pos=None, tok_in: int = 0, tok_out: int = 0, tok_shift: int = 0,
+         ln_stats=None, ln_colsum=None, ln_eps: float = 1e-6, stats_out=None, xb_out=None) -> Optional[torch.Tensor]:
+    """C = a[M,K] @ w[N,K]^T with the fused epilogue `mode` (see include/bridgelang_b200.h).
+
+    ln_stats [parts, M, 2] + ln_colsum [N]: LayerNorm folded into a BIAS / BIAS_GELU GEMM (a = bf16 copy of the
+    un-normalised rows, w = W·diag(ln_w), bias = b + W·ln_b).  stats_out [gemm_stats_parts(N), M, 2] / xb_out [M, N]:
+    what a RESIDUAL GEMM emits for such a consumer."""
+    _need_cuda(a, w, bias, gamma, resid, out, pos, ln_stats, ln_colsum, stats_out, xb_out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -64,10 +69,36 @@ def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, 
     e.ld_out = out.stride(0) if out is not None else 0
     e.out_col_off = out_col_off
     e.tok_in, e.tok_out, e.tok_shift = tok_in, tok_out, tok_shift
+    if ln_stats is not None:
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape[1] == M
+        e.ln_stats, e.ln_colsum, e.ln_parts, e.ln_eps = ln_stats.data_ptr(), _ptr(ln_colsum), ln_stats.shape[0], ln_eps
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous()
+        assert tuple(stats_out.shape) == (gemm_stats_parts(N), M, 2)
+        e.stats_out = stats_out.data_ptr()
+    if xb_out is not None:
+        assert xb_out.dtype == torch.bfloat16 and xb_out.stride(1) == 1 and tuple(xb_out.shape) == (M, N)
+        e.xb_out, e.ld_xb = xb_out.data_ptr(), xb_out.stride(0)
     lib = _lib.load()
     _lib.check(lib.blb_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, mode, C.byref(e),
                                  _stream()), "gemm")
     return out
+
+
+def gemm_stats_parts(n: int) -> int:
+    """(sum, sumsq) pairs per row that an EPI_RESIDUAL GEMM with N = n writes into `stats_out`."""
+    return int(_lib.load().blb_gemm_stats_parts(int(n)))
+
+
+def rowstats_cast(x: torch.Tensor, parts: int):
+    """fp32 rows → (bf16 copy, stats [parts, rows, 2] with the full-row (sum, sumsq) in part 0)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((parts, x.shape[0], 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().blb_rowstats_cast(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), stats.data_ptr(),
+                                             parts, x.shape[0], x.shape[1], _stream()), "rowstats_cast")
+    return y, stats
 
 
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
@@ -180,4 +211,25 @@ def timing_collect() -> dict:
         ms, work, n = C.c_double(), C.c_double(), C.c_longlong()
         _lib.check(lib.blb_timing_collect(i, C.byref(ms), C.byref(work), C.byref(n)), "timing_collect")
         out[name] = {"ms": ms.value, "work": work.value, "launches": n.value}
+    return out
+
+
+def timing_records(max_records: int = 4096) -> list:
+    """Every instrumented launch since the last reset, in launch order: dicts {cat, ms, work} and, for GEMMs,
+    {mode, ln_folded, emits_stats, N, K} decoded from the tag.  Call after torch.cuda.synchronize()."""
+    cat = (C.c_int * max_records)()
+    tag = (C.c_longlong * max_records)()
+    ms = (C.c_double * max_records)()
+    work = (C.c_double * max_records)()
+    n = _lib.load().blb_timing_records(max_records, cat, tag, ms, work)
+    if n < 0:
+        raise RuntimeError(f"blb_timing_records failed: {n}")
+    out = []
+    for i in range(n):
+        r = {"cat": TIMING_CATEGORIES[cat[i]], "ms": ms[i], "work": work[i]}
+        if cat[i] == 0:
+            t = tag[i]
+            r.update(mode=t >> 44, ln_folded=(t >> 43) & 1, emits_stats=(t >> 42) & 1, N=(t >> 20) & 0xFFFFF,
+                     K=t & 0xFFFFF)
+        out.append(r)
     return out

@@ -15,6 +15,7 @@ change.  The arithmetic is NOT timm/PyTorch: `forward` hands raw device pointers
 from __future__ import annotations
 
 import ctypes as C
+import os
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
 from functools import partial
@@ -137,6 +138,7 @@ class VisionTransformer(nn.Module):
         self.requires_grad_(False)
         self.eval()
         self._packed: Optional[_PackedTower] = None
+        self.ln_folded = os.environ.get("BLB_LN_EXPLICIT") is None   # see _PackedTower; set before the first forward
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_packed())
 
     # -- packing ------------------------------------------------------------------------------------
@@ -225,6 +227,16 @@ class _PackedTower:
             prefix.append(vit.reg_token.detach().reshape(cfg.reg_tokens, D))
         self.prefix = f32(torch.cat(prefix, dim=0)) if prefix else None
 
+        # norm1 → attn.qkv and norm2 → mlp.fc1 folded (default): LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·colsum(W')) + b'
+        # with W' = W·diag(ln_w) rounded to bf16 once, colsum over the ROUNDED W' (so the mean term cancels exactly
+        # what the tensor cores accumulate) and b' = b + W·ln_b in fp32.  BLB_LN_EXPLICIT=1 keeps the LayerNorm kernel.
+        self.ln_folded = vit.ln_folded
+
+        def fold(w: torch.Tensor, b: torch.Tensor, ln: nn.LayerNorm):
+            w32, lw, lb = w.float(), ln.weight.detach().float().to(dev), ln.bias.detach().float().to(dev)
+            wf = b16(w32 * lw[None, :])
+            return wf, f32(b.float() + w32 @ lb), f32(wf.float().sum(dim=1))
+
         n_blocks = cfg.n_needed_blocks
         self.blocks = (_lib.BlockWeights * n_blocks)()
         for i in range(n_blocks):
@@ -236,11 +248,19 @@ class _PackedTower:
             fc1_b[:Hm] = blk.mlp.fc1.bias.detach().float()
             fc2_w = torch.zeros((D, Hp), dtype=torch.float32, device=dev)
             fc2_w[:, :Hm] = blk.mlp.fc2.weight.detach().float()
-            bw.ln1_w, bw.ln1_b = f32(blk.norm1.weight).data_ptr(), f32(blk.norm1.bias).data_ptr()
-            bw.qkv_w, bw.qkv_b = b16(blk.attn.qkv.weight).data_ptr(), f32(blk.attn.qkv.bias).data_ptr()
             bw.proj_w, bw.proj_b = b16(blk.attn.proj.weight).data_ptr(), f32(blk.attn.proj.bias).data_ptr()
-            bw.ln2_w, bw.ln2_b = f32(blk.norm2.weight).data_ptr(), f32(blk.norm2.bias).data_ptr()
-            bw.fc1_w, bw.fc1_b = b16(fc1_w).data_ptr(), f32(fc1_b).data_ptr()
+            if self.ln_folded:
+                qw, qb, qs = fold(blk.attn.qkv.weight.detach().to(dev), blk.attn.qkv.bias.detach().to(dev), blk.norm1)
+                fw, fb, fs = fold(fc1_w, fc1_b, blk.norm2)
+                bw.qkv_w, bw.qkv_b, bw.qkv_colsum = qw.data_ptr(), qb.data_ptr(), qs.data_ptr()
+                bw.fc1_w, bw.fc1_b, bw.fc1_colsum = fw.data_ptr(), fb.data_ptr(), fs.data_ptr()
+                bw.ln1_w = bw.ln1_b = bw.ln2_w = bw.ln2_b = None
+            else:
+                bw.ln1_w, bw.ln1_b = f32(blk.norm1.weight).data_ptr(), f32(blk.norm1.bias).data_ptr()
+                bw.qkv_w, bw.qkv_b = b16(blk.attn.qkv.weight).data_ptr(), f32(blk.attn.qkv.bias).data_ptr()
+                bw.ln2_w, bw.ln2_b = f32(blk.norm2.weight).data_ptr(), f32(blk.norm2.bias).data_ptr()
+                bw.fc1_w, bw.fc1_b = b16(fc1_w).data_ptr(), f32(fc1_b).data_ptr()
+                bw.qkv_colsum = bw.fc1_colsum = None
             bw.fc2_w, bw.fc2_b = b16(fc2_w).data_ptr(), f32(blk.mlp.fc2.bias).data_ptr()
             if cfg.layer_scale:
                 bw.ls1, bw.ls2 = f32(blk.ls1.value).data_ptr(), f32(blk.ls2.value).data_ptr()
@@ -255,6 +275,7 @@ class _PackedTower:
         s.pos_embed = f32(vit.pos_embed.reshape(NUM_PATCHES, D)).data_ptr()
         s.prefix = self.prefix.data_ptr() if self.prefix is not None else None
         s.blocks_host = C.cast(self.blocks, C.POINTER(_lib.BlockWeights))
+        s.ln_folded = 1 if self.ln_folded else 0
         self.struct = s
 
 

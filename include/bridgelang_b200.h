@@ -53,6 +53,18 @@ typedef struct blb_epilogue {
   int32_t tok_in;      /* row remap per image: src row b*tok_in+t -> dst row b*tok_out+t+tok_shift; 0 = identity */
   int32_t tok_out;
   int32_t tok_shift;
+  /* LayerNorm folded into the neighbouring GEMMs (timm Block.norm1 -> attn.qkv, Block.norm2 -> mlp.fc1):
+   * consumer (BIAS / BIAS_GELU), ln_stats != NULL: A is the bf16 copy of the UN-normalised fp32 rows, W holds
+   * W*diag(ln_w), bias holds b + W*ln_b, and out = rstd_m*(acc - mean_m*ln_colsum_n) + bias_n, where mean/rstd of
+   * row m come from ln_parts partial (sum, sum-of-squares) float pairs. */
+  const float* ln_stats;   /* [ln_parts, M, 2] or NULL */
+  const float* ln_colsum;  /* [N] sum_k W'[n,k] over the bf16-rounded folded weight */
+  int32_t ln_parts;
+  float ln_eps;
+  /* producer (RESIDUAL): partial statistics [blb_gemm_stats_parts(N), M, 2] and bf16 copy [M, ld_xb] of the new rows */
+  float* stats_out;        /* or NULL */
+  void* xb_out;            /* or NULL */
+  int32_t ld_xb;
 } blb_epilogue;
 
 /* One timm `Block` (vision_transformer.Block as instantiated at dinosiglip_vit.py:50-58). */
@@ -65,6 +77,10 @@ typedef struct blb_block_weights {
   const void* fc1_w;  const float* fc1_b;       /* mlp.fc1 bf16 [Hm_pad, D], fp32 [Hm_pad] (rows >= Hm zero) */
   const void* fc2_w;  const float* fc2_b;       /* mlp.fc2 bf16 [D, Hm_pad] (cols >= Hm zero), fp32 [D] */
   const float* ls2;                             /* ls2.gamma or NULL */
+  /* only when blb_vit_weights.ln_folded: qkv_w = W*diag(ln1_w), qkv_b = b + W*ln1_b (same for fc1 with ln2), and
+   * these hold sum_k of the bf16-rounded folded rows: fp32 [3D] / [Hm_pad].  ln1_ / ln2_ pointers are then unused. */
+  const float* qkv_colsum;
+  const float* fc1_colsum;
 } blb_block_weights;
 
 /* One timm VisionTransformer restricted to what get_intermediate_layers(n={depth-2}) needs. */
@@ -82,6 +98,8 @@ typedef struct blb_vit_weights {
   const float* pos_embed;    /* [256, D] */
   const float* prefix;       /* [n_prefix, D]: cls_token then reg_token rows, or NULL */
   const blb_block_weights* blocks_host; /* HOST array of n_blocks entries (device pointers inside) */
+  int32_t ln_folded;  /* 1: no LayerNorm kernel - norm1/norm2 are folded into the qkv / fc1 GEMMs and their statistics come
+                       * from the producing GEMM's epilogue; 0: explicit LayerNorm kernel before qkv / fc1 */
 } blb_vit_weights;
 
 /* prismatic/util/nn_utils.py:37-53 FusedMLPProjector == extern/hf/modeling_prismatic.py:146-158 fc1/fc2/fc3 */
@@ -113,12 +131,20 @@ void blb_debug_attention_trace(void* device_buffer);
 void blb_timing_enable(int on);
 void blb_timing_reset(void);
 int blb_timing_collect(int category, double* ms, double* work, long long* launches);
+/* every record since the last reset, in launch order (call after synchronising): returns the number written (<= max_records)
+ * or a negated cudaError_t.  GEMM tag = mode << 44 | ln-folded consumer << 43 | stats/xb producer << 42 | N << 20 | K. */
+int blb_timing_records(int max_records, int* category, long long* tag, double* ms, double* work);
 
 /* ---- primitive operators (each replaces one library call of the reference; used by the parity tests) --- */
 /* C = A[M,K] (bf16, pitch lda) x W[N,K]^T (bf16, pitch ldw) with a fused epilogue.
  * Replaces nn.Linear (+GELU / +LayerScale+residual) reached via timm Attention/Mlp and nn_utils.py:42-48. */
 int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int mode,
                   const blb_epilogue* epi, void* stream);
+/* partial-statistics pairs per row that a BLB_EPI_RESIDUAL launch with this N writes to stats_out (0: N unsupported) */
+int blb_gemm_stats_parts(int N);
+/* fp32 rows -> bf16 copy + (sum, sum of squares) in pair 0 of `parts` pairs per row (others zero): primes the folded chain */
+int blb_rowstats_cast(const float* x, int ldx, void* y_bf16, int ldy, float* stats, int parts, int rows, int D,
+                      void* stream);
 /* timm LayerNorm(D, eps) on fp32 rows -> bf16 rows (Block.norm1 / norm2). */
 int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void* y_bf16, int ldy, int rows, int D,
                   float eps, void* stream);

@@ -156,3 +156,87 @@ def test_im2col_matches_unfold_and_conv_weight_order(ops):
     out = ops.gemm(cols, wp, ops.EPI_BIAS, bias=bias)
     conv = F.conv2d(px.float(), w.float(), stride=14).flatten(2).transpose(1, 2).reshape(-1, 128)
     assert _rel(out, conv) < 1.5 * BF16_EPS
+
+
+# ---- LayerNorm folded into the neighbouring GEMMs ------------------------------------------
+def _stats_ref(x):
+    return torch.stack([x.sum(dim=1), (x * x).sum(dim=1)], dim=1)
+
+
+@pytest.mark.parametrize("D", [1024, 1152])
+def test_rowstats_cast(ops, D):
+    g = _gen(D + 1)
+    x = torch.randn(700, D, device="cuda", generator=g) * 2 + 0.5
+    parts = ops.gemm_stats_parts(D)
+    assert parts == {1024: 8, 1152: 12}[D]
+    xb, stats = ops.rowstats_cast(x, parts)
+    assert torch.equal(xb, x.bfloat16())
+    assert stats.shape == (parts, 700, 2)
+    assert torch.allclose(stats.sum(dim=0), _stats_ref(x), rtol=1e-5, atol=1e-3)
+    assert bool((stats[1:] == 0).all())
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("N,K", [(1024, 512), (1152, 4352)])
+def test_gemm_residual_emits_stats_and_bf16_copy(ops, ctas, N, K):
+    """Producer side: the EPI_RESIDUAL epilogue also writes the bf16 copy of the new rows and, per epilogue-warp column
+    span, the partial (sum, sum of squares) of the exact fp32 values it stored."""
+    ops.set_gemm_cta_group(ctas)
+    M = 3 * 261
+    g = _gen(N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    resid0 = torch.randn(M, N, device="cuda", generator=g) + 0.3
+    resid = resid0.clone()
+    parts = ops.gemm_stats_parts(N)
+    stats = torch.full((parts, M, 2), float("nan"), device="cuda")
+    xb = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, ops.EPI_RESIDUAL, bias=bias, gamma=gamma, resid=resid, stats_out=stats, xb_out=xb)
+    ref = resid0 + gamma * (a.float() @ w.float().t() + bias)
+    assert _rel(resid, ref) < 2e-5
+    assert torch.equal(xb, resid.bfloat16())                    # the copy is the rounding of what was stored
+    span = N // parts
+    want = torch.stack([_stats_ref(resid[:, p * span:(p + 1) * span]) for p in range(parts)], dim=0)
+    assert torch.allclose(stats, want, rtol=1e-5, atol=1e-4)
+    ops.set_gemm_cta_group(0)
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("mode_gelu", [False, True])
+@pytest.mark.parametrize("D,N", [(1024, 3072), (1152, 4352)])
+def test_gemm_with_folded_layernorm_matches_layernorm_then_linear(ops, ctas, mode_gelu, D, N):
+    """Consumer side against timm's own formulation: Linear(LayerNorm(x)) [+ GELU] in fp32 — row means far from zero,
+    one near-constant row (eps matters) and non-trivial LN affine parameters."""
+    ops.set_gemm_cta_group(ctas)
+    M = 777
+    g = _gen(D + N)
+    x = torch.randn(M, D, device="cuda", generator=g) * 1.5 + torch.randn(M, 1, device="cuda", generator=g)
+    x[5] = 2.0 + 1e-3 * torch.randn(D, device="cuda", generator=g)
+    ln_w = torch.rand(D, device="cuda", generator=g) + 0.5
+    ln_b = torch.randn(D, device="cuda", generator=g) * 0.1
+    W = torch.randn(N, D, device="cuda", generator=g) * 0.03
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    # pack exactly as vision._PackedTower does
+    wf = (W * ln_w[None, :]).bfloat16()
+    colsum = wf.float().sum(dim=1)
+    bf = b + W @ ln_b
+    parts = ops.gemm_stats_parts(D)
+    xb, stats = ops.rowstats_cast(x, parts)
+    out = ops.gemm(xb, wf, ops.EPI_BIAS_GELU if mode_gelu else ops.EPI_BIAS, bias=bf, ln_stats=stats,
+                   ln_colsum=colsum, ln_eps=1e-6).float()
+    ref = F.linear(F.layer_norm(x, (D,), ln_w, ln_b, 1e-6), W, b)
+    if mode_gelu:
+        ref = F.gelu(ref)
+    ok = torch.ones(M, dtype=torch.bool, device="cuda")
+    ok[5] = False                                               # the near-constant row is checked separately below
+    assert _rel(out[ok], ref[ok]) < 8e-3                        # bf16 rounding of x and W' (K = 1024/1152 terms)
+    # explicit-LN path on the same data for comparison: the fold must be no worse than ~2x of it
+    xn = ops.layernorm(x, ln_w, ln_b, 1e-6)
+    base = ops.gemm(xn, W.bfloat16(), ops.EPI_BIAS_GELU if mode_gelu else ops.EPI_BIAS, bias=b).float()
+    assert _rel(out[ok], ref[ok]) < 2.0 * _rel(base[ok], ref[ok]) + 1e-3
+    # near-constant row: rstd ~ 1/sqrt(1e-6 + 1e-6); with eps = 1e-5 the output would be ~2.3x smaller.  bf16 rounding of
+    # x = 2.0 + 1e-3·noise destroys that row's signal in ANY bf16-operand formulation, so only its scale is pinned.
+    assert out[5].abs().max() < 50 * ref.abs().max()
+    ops.set_gemm_cta_group(0)

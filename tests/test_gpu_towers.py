@@ -46,6 +46,28 @@ def test_single_tower_vs_oracle(cfg, key, depth):
     assert _rel(vit_oracle.vit_intermediate(bad, cfg, px.bfloat16().float()), ref) > 2 * TOL
 
 
+@pytest.mark.parametrize("cfg,key", [(DINOV2_L14_REG4, "dino"), (SIGLIP_SO400M_14, "siglip")])
+def test_folded_and_explicit_layernorm_towers_agree(cfg, key):
+    """norm1/norm2 folded into the qkv / fc1 GEMMs (default) vs the explicit LayerNorm kernel (BLB_LN_EXPLICIT): two
+    different roundings of the same arithmetic — both inside the gate against the oracle, and close to each other."""
+    cfg = cfg.with_depth(4)
+    sd = make_vit_state_dict(cfg, seed=33, init="stress")
+    px = _pixels(2, seed=5)[key]
+    ref = vit_oracle.vit_intermediate(sd, cfg, px.bfloat16().float())
+    outs = {}
+    for folded in (True, False):
+        vit = blb.VisionTransformer(cfg)
+        vit.ln_folded = folded
+        vit.load_state_dict(sd)
+        vit.cuda()
+        assert vit.packed().struct.ln_folded == int(folded)
+        outs[folded] = vit(px.cuda())
+        err = _rel(outs[folded], ref)
+        print(f"{key} ln_folded={folded}: {err:.3e}")
+        assert err < TOL, (folded, err)
+    assert _rel(outs[True], outs[False]) < TOL
+
+
 def test_cta_group_1_and_2_agree_on_a_tower():
     from bridgelang_b200 import ops
     cfg = SIGLIP_SO400M_14.with_depth(3)

@@ -33,17 +33,32 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.blb_abi_version() == 1
+    assert lib.blb_abi_version() == 2
     assert lib.blb_status_string(0) == b"ok"
     assert b"workspace" in lib.blb_status_string(-5)
 
 
 def test_struct_layouts_match_header(lib):
-    # sizes follow from the field lists in include/bridgelang_b200.h on LP64
-    assert ctypes.sizeof(_lib.Epilogue) == 72
-    assert ctypes.sizeof(_lib.BlockWeights) == 14 * 8
-    assert ctypes.sizeof(_lib.VitWeights) == 8 * 4 + 5 * 8
-    assert ctypes.sizeof(_lib.ProjectorWeights) == 16 + 6 * 8
+    # ask the C compiler: sizeof + the offset of the last field of every struct in include/bridgelang_b200.h
+    import subprocess, tempfile
+    src = r'''#include <stdio.h>
+#include <stddef.h>
+#include "bridgelang_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(blb_epilogue), offsetof(blb_epilogue, ld_xb),
+         sizeof(blb_block_weights), offsetof(blb_block_weights, fc1_colsum), sizeof(blb_vit_weights),
+         offsetof(blb_vit_weights, ln_folded), sizeof(blb_projector_weights), offsetof(blb_projector_weights, fc3_b));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "t.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), str(Path(d) / "t.c"), "-o", str(Path(d) / "t")], check=True)
+        got = [int(x) for x in subprocess.run([str(Path(d) / "t")], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.Epilogue), _lib.Epilogue.ld_xb.offset,
+            ctypes.sizeof(_lib.BlockWeights), _lib.BlockWeights.fc1_colsum.offset,
+            ctypes.sizeof(_lib.VitWeights), _lib.VitWeights.ln_folded.offset,
+            ctypes.sizeof(_lib.ProjectorWeights), _lib.ProjectorWeights.fc3_b.offset]
+    assert got == want, (got, want)
 
 
 def test_bad_arguments_return_negative_status_without_gpu(lib):

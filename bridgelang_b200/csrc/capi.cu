@@ -52,6 +52,35 @@ int check_vit(const blb_vit_weights* w) {
   return 0;
 }
 
+#define BLB_CUDA(expr)                                         \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return static_cast<int>(_e);        \
+  } while (0)
+
+// side stream + fork/join events for running the two towers concurrently (one set per device, created lazily;
+// BLB_NO_TOWER_OVERLAP=1 runs them back to back on the caller's stream)
+const bool g_tower_overlap = getenv("BLB_NO_TOWER_OVERLAP") == nullptr;
+struct TowerOverlap {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+TowerOverlap* tower_overlap_ctx() {
+  static TowerOverlap ctx[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  TowerOverlap& c = ctx[dev];
+  if (c.side == nullptr) {
+    if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) {
+      c.side = nullptr;
+      return nullptr;
+    }
+  }
+  return &c;
+}
+
 #define BLB_TRY(expr)        \
   do {                       \
     int _rc = (expr);        \
@@ -388,7 +417,8 @@ int blb_projector_forward(const blb_projector_weights* w, const void* x, int ldx
 size_t blb_fused_workspace_bytes(const blb_vit_weights* dino, const blb_vit_weights* siglip,
                                  const blb_projector_weights* proj, int batch) {
   if (dino == nullptr || siglip == nullptr || batch <= 0) return 0;
-  size_t s = std::max(tower_ws(dino, batch).total, tower_ws(siglip, batch).total);
+  // the two towers may run concurrently (tower_overlap) → disjoint regions; the projector runs after both and aliases them
+  size_t s = align_up(tower_ws(dino, batch).total) + tower_ws(siglip, batch).total;
   if (proj != nullptr) s = std::max(s, projector_ws(proj, batch * PATCHES));
   return s;
 }
@@ -403,9 +433,27 @@ int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_v
   const int fused_dim = dino->dim + siglip->dim;
   if (proj != nullptr && proj->in_dim != fused_dim) return BLB_ERR_SHAPE;
   cudaStream_t st = as_stream(stream);
-  // dinosiglip_vit.py:144-147: dino patches | siglip patches, concatenated on the channel dim
-  BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, workspace_bytes, st));
-  BLB_TRY(tower_forward(siglip, pixels_siglip, batch, features, fused_dim, dino->dim, workspace, workspace_bytes, st));
+  // dinosiglip_vit.py:144-147: dino patches | siglip patches, concatenated on the channel dim.
+  // The reference runs the towers one after the other; they are independent until the concat, so here the SigLIP tower
+  // runs on a side stream next to the DINOv2 tower: every persistent kernel's ragged last wave and launch ramp is
+  // filled by CTAs of the other tower instead of idling SMs.  (Serial when per-launch timing is on, so that the
+  // per-kernel numbers of bench.py's instrumented pass stay clean.)
+  const size_t dino_bytes = align_up(tower_ws(dino, batch).total);
+  uint8_t* ws_siglip = static_cast<uint8_t*>(workspace) + dino_bytes;
+  TowerOverlap* ov = (g_tower_overlap && !timing_enabled()) ? tower_overlap_ctx() : nullptr;
+  if (ov != nullptr) {
+    BLB_CUDA(cudaEventRecord(ov->fork, st));
+    BLB_CUDA(cudaStreamWaitEvent(ov->side, ov->fork, 0));
+    BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, dino_bytes, st));
+    BLB_TRY(tower_forward(siglip, pixels_siglip, batch, features, fused_dim, dino->dim, ws_siglip,
+                          workspace_bytes - dino_bytes, ov->side));
+    BLB_CUDA(cudaEventRecord(ov->join, ov->side));
+    BLB_CUDA(cudaStreamWaitEvent(st, ov->join, 0));
+  } else {
+    BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, dino_bytes, st));
+    BLB_TRY(tower_forward(siglip, pixels_siglip, batch, features, fused_dim, dino->dim, ws_siglip,
+                          workspace_bytes - dino_bytes, st));
+  }
   if (proj != nullptr)
     BLB_TRY(projector_forward(proj, features, fused_dim, batch * PATCHES, projected, proj->out_dim, 0, 0, 0, workspace,
                               workspace_bytes, st));

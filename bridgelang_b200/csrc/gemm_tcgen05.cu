@@ -36,18 +36,20 @@ constexpr int RCHUNK_BYTES = 32 * 32 * 4;   // one epilogue warp's [32 rows x 32
 constexpr int OCHUNK_BYTES = 32 * 32 * 2;   // one epilogue warp's [32 rows x 32 cols] bf16 output staging chunk
 constexpr int VEC_BYTES = 2 * 128 * 4;      // one epilogue warp's per-tile copy of two per-column fp32 vectors (<= 128 cols)
 
-template <int BN, int CTAS, bool RTMA = false, bool OBUF = false>
+template <int BN, int CTAS, int RTMA = 0, bool OBUF = false>
 struct GemmCfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of W this CTA stages per k-block
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // RTMA: every epilogue warp owns two TMA-fed residual chunk buffers (prefetched two chunks ahead)
+  // RTMA = 1 | 2: every epilogue warp owns that many TMA-fed residual chunk buffers (prefetched RTMA chunks ahead).
+  //   2 for short-K GEMMs (out-proj: the epilogue is on the critical path), 1 for deep-K GEMMs (fc2: the tile takes
+  //   4x longer than its epilogue, and the 32 KB saved buy a fifth operand stage for the HBM-streamed A operand)
   // OBUF: every epilogue warp owns one bf16 staging chunk used to transpose its row-per-lane results into
   //       row-contiguous (coalesced) global stores
   // every epilogue warp also keeps this tile's slice of bias and of gamma / LN column sums in smem (VEC_BYTES): one
   // coalesced load per tile, issued before the accumulator is ready, instead of 8-16 dependent LDGs per 32-column chunk
-  static constexpr int STAGE_EPI_BYTES = RTMA ? NUM_EPI_WARPS * 2 * RCHUNK_BYTES : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : 0);
+  static constexpr int STAGE_EPI_BYTES = RTMA ? NUM_EPI_WARPS * RTMA * RCHUNK_BYTES : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : 0);
   static constexpr int EPI_BYTES = STAGE_EPI_BYTES + NUM_EPI_WARPS * VEC_BYTES;
   static constexpr int STAGES = (200 * 1024 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 512;                    // 2 accumulator stages of BN (<=256) columns
@@ -68,7 +70,7 @@ __device__ __forceinline__ bool map_row(const GemmEpilogue& e, int row, int& dst
   return t2 >= 0 && t2 < e.tok_out;
 }
 
-template <int BN, int CTAS, int MODE, bool RTMA>
+template <int BN, int CTAS, int MODE, int RTMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K, GemmEpilogue epi) {
@@ -119,7 +121,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tempty_bar[i], CTAS * NUM_EPI_WARPS);
     }
     if (RTMA)
-      for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(&rld_bar[i], 1);
+      for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(&rld_bar[i], 1);   // [8][2]; only [.][0] used when RTMA == 1
     fence_mbar_init();
   }
   if (warp == W_ALLOC) {
@@ -214,9 +216,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     // RTMA: flat sequence seq = local_tile * CHUNKS + chunk; residual chunk `seq` lands in buffer seq & 1 of this
-    // warp, its TMA is issued two sequence steps ahead (i.e. possibly already for the next tile).
+    // warp, its TMA is issued RB sequence steps ahead (i.e. possibly already for the next tile).
     const uint32_t vec_s = smem_u32(smem_r) + Cfg::STAGE_EPI_BYTES + ew * VEC_BYTES;
-    uint8_t* rbuf = smem_r + ew * 2 * RCHUNK_BYTES;
+    constexpr int RB = RTMA > 0 ? RTMA : 1;
+    uint8_t* rbuf = smem_r + ew * RB * RCHUNK_BYTES;
     uint64_t* rbar = rld_bar + ew * 2;
     auto issue_resid = [&](int sq) {
       const int lt = sq / CHUNKS, c = sq - lt * CHUNKS;
@@ -226,13 +229,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int mb = tl / n_tiles, nb = tl - mb * n_tiles;
       const int r0 = mb * tile_m + static_cast<int>(cta_rank) * BM + quarter * 32;
       const int c0 = nb * BN + half * COLS_PER_WARP + c * 32;
-      mbar_expect_tx(&rbar[sq & 1], RCHUNK_BYTES);
-      tma_load_2d(rbuf + (sq & 1) * RCHUNK_BYTES, &tmap_r, &rbar[sq & 1], c0, r0);
+      mbar_expect_tx(&rbar[sq % RB], RCHUNK_BYTES);
+      tma_load_2d(rbuf + (sq % RB) * RCHUNK_BYTES, &tmap_r, &rbar[sq % RB], c0, r0);
     };
     int seq = 0;
     if (RTMA && lane == 0) {
       issue_resid(0);
-      issue_resid(1);
+      if (RB == 2) issue_resid(1);
     }
     for (int tile_i = first_tile; tile_i < num_tiles; tile_i += tile_step) {
       const int tile = epi.reverse ? num_tiles - 1 - tile_i : tile_i;
@@ -316,8 +319,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float xres[RTMA ? 32 : 1];
         if constexpr (RTMA) {
           // this lane's row of the TMA-staged residual chunk (128-byte rows, 128B-swizzled → conflict-free)
-          mbar_wait(&rbar[seq & 1], static_cast<uint32_t>((seq >> 1) & 1));
-          const uint32_t src = smem_u32(rbuf) + (seq & 1) * RCHUNK_BYTES + lane * 128;
+          mbar_wait(&rbar[seq % RB], static_cast<uint32_t>((seq / RB) & 1));
+          const uint32_t src = smem_u32(rbuf) + (seq % RB) * RCHUNK_BYTES + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 x4 = lds128(src + ((j ^ (lane & 7)) << 4));
@@ -440,7 +443,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if constexpr (RTMA) {
             // write the updated row back into the (already consumed) residual chunk in place, then store the
             // chunk transposed: each store instruction writes 4 rows x 128 contiguous bytes
-            const uint32_t cb = smem_u32(rbuf) + (seq & 1) * RCHUNK_BYTES;
+            const uint32_t cb = smem_u32(rbuf) + (seq % RB) * RCHUNK_BYTES;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               sts128(cb + lane * 128 + ((j ^ (lane & 7)) << 4),
@@ -475,7 +478,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // generic proxy → fence, converge, then lane 0 issues the TMA for the chunk two steps ahead.
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) issue_resid(seq + 2);
+            if (lane == 0) issue_resid(seq + RB);
             ++seq;
           }
         }
@@ -626,7 +629,7 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, int CTAS, int MODE, bool RTMA>
+template <int BN, int CTAS, int MODE, int RTMA>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, int M, int N, int K,
                   const GemmEpilogue& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, RTMA, (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU)>;
@@ -669,17 +672,19 @@ template <int BN, int CTAS>
 static int launch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                        const GemmEpilogue& epi, cudaStream_t s) {
   switch (mode) {
-    case EPI_BIAS: return launch<BN, CTAS, EPI_BIAS, false>(ta, tb, ta, M, N, K, epi, s);
-    case EPI_BIAS_GELU: return launch<BN, CTAS, EPI_BIAS_GELU, false>(ta, tb, ta, M, N, K, epi, s);
-    case EPI_PATCH: return launch<BN, CTAS, EPI_PATCH, false>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_BIAS: return launch<BN, CTAS, EPI_BIAS, 0>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_BIAS_GELU: return launch<BN, CTAS, EPI_BIAS_GELU, 0>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_PATCH: return launch<BN, CTAS, EPI_PATCH, 0>(ta, tb, ta, M, N, K, epi, s);
     case EPI_RESIDUAL: {
-      if (g_resid_direct) return launch<BN, CTAS, EPI_RESIDUAL, false>(ta, tb, ta, M, N, K, epi, s);
+      if (g_resid_direct) return launch<BN, CTAS, EPI_RESIDUAL, 0>(ta, tb, ta, M, N, K, epi, s);
       CUtensorMap tr;   // fp32 residual stream [M, N] → [32 x 32] boxes, 128B-swizzled rows
       int rc = make_tmap_2d(&tr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.resid, static_cast<uint64_t>(M),
                             static_cast<uint64_t>(N), static_cast<uint64_t>(epi.ld_resid), 32, 32,
                             CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc != 0) return rc;
-      return launch<BN, CTAS, EPI_RESIDUAL, true>(ta, tb, tr, M, N, K, epi, s);
+      static const int deep_k = getenv("BLB_RESID_DEEPK") ? atoi(getenv("BLB_RESID_DEEPK")) : 2048;   // A/B switch
+      if (K >= deep_k) return launch<BN, CTAS, EPI_RESIDUAL, 1>(ta, tb, tr, M, N, K, epi, s);
+      return launch<BN, CTAS, EPI_RESIDUAL, 2>(ta, tb, tr, M, N, K, epi, s);
     }
   }
   return BLB_ERR_ARG;

@@ -128,7 +128,8 @@ def test_layernorm(ops, D):
     assert (y[7:8] - ref[7:8]).abs().max() < 0.1 * (wrong_eps - ref[7:8]).abs().max()
 
 
-@pytest.mark.parametrize("B,T,H,hd", [(3, 261, 16, 64), (3, 256, 16, 72), (2, 64, 2, 64), (1, 7, 1, 72)])
+@pytest.mark.parametrize("B,T,H,hd", [(3, 261, 16, 64), (3, 256, 16, 72), (2, 64, 2, 64), (1, 7, 1, 72), (2, 257, 3, 64),
+                                    (2, 272, 2, 64), (5, 270, 16, 64)])
 def test_attention(ops, B, T, H, hd):
     g = _gen(T + hd)
     D = H * hd

@@ -7,11 +7,13 @@ Status translation follows SURVEY.md §8b (non-zero status → RuntimeError).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libbridgelang_b200.so"
+# BLB_LIB: development override (A/B of two builds on one box); the product path is the in-tree library
+LIB_PATH = Path(os.environ["BLB_LIB"]) if os.environ.get("BLB_LIB") else PKG_DIR / "libbridgelang_b200.so"
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2

@@ -51,7 +51,11 @@ struct GemmCfg {
   // coalesced load per tile, issued before the accumulator is ready, instead of 8-16 dependent LDGs per 32-column chunk
   static constexpr int STAGE_EPI_BYTES = RTMA ? NUM_EPI_WARPS * RTMA * RCHUNK_BYTES : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : 0);
   static constexpr int EPI_BYTES = STAGE_EPI_BYTES + NUM_EPI_WARPS * VEC_BYTES;
-  static constexpr int STAGES = (200 * 1024 - EPI_BYTES) / STAGE_BYTES;
+  // one CTA per SM: spend all 227 KB of shared memory on operand stages (the deeper ring lets the TMA producer run
+  // further into the next tile while the current one drains)
+  static constexpr int SMEM_MAX = 227 * 1024;
+  static constexpr int STAGES_MAX = (SMEM_MAX - EPI_BYTES - 1024 - 512) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
   static constexpr int TMEM_COLS = 512;                    // 2 accumulator stages of BN (<=256) columns
   static constexpr int ACC_STRIDE = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;

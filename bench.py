@@ -41,6 +41,18 @@ UNIT = "images/s"
 WORKLOAD = "prism-dinosiglip-224px featurizer + FusedMLPProjector, bf16, batch 256 synthetic 224px frames per GPU"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r01_ncu_full_c_kernels.md), keyed like ops.timing_records: (mode, N, K, ln_folded, emits_stats)
+NCU_DRAM_BYTES_PER_LAUNCH = {
+    (0, 3072, 1024, 1, 0): 147.46e6 + 362.11e6,     # DINOv2 qkv   (algorithmic: A 137 + W 6 + out 410 MB)
+    (1, 4096, 1024, 1, 0): 149.58e6 + 496.06e6,     # DINOv2 fc1   (A 137 + W 8 + out 547 MB)
+    (2, 1024, 4096, 0, 1): 928.53e6 + 378.77e6,     # DINOv2 fc2   (A 547 + W 8 + resid 274 r + 274 w + bf16 copy 137 MB)
+    (2, 1024, 1024, 0, 1): 415.44e6 + 362.06e6,     # DINOv2 proj  (A 137 + W 2 + resid 274 r + 274 w + bf16 copy 137 MB)
+    (1, 4352, 1152, 1, 0): 167.40e6 + 524.24e6,     # SigLIP fc1   (A 151 + W 10 + out 570 MB)
+    (2, 1152, 4352, 0, 1): 948.67e6 + 425.22e6,     # SigLIP fc2   (A 570 + W 10 + resid 302 r + 302 w + bf16 copy 151 MB)
+}
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -192,6 +204,7 @@ def run_gpu(args) -> None:
     # this rank's contiguous slice of the global synthetic batch (different frames per rank)
     frames = synthetic_frames(B, seed=1000 + rank)
     px_host = {k: v.to(torch.bfloat16).pin_memory() for k, v in normalize_frames(frames).items()}
+    frames_host = frames.contiguous().pin_memory()
     px_dev = {k: v.to(device, non_blocking=True) for k, v in px_host.items()}
     torch.cuda.synchronize()
 
@@ -205,6 +218,14 @@ def run_gpu(args) -> None:
         if args.gather and distributed:
             out = gather_prefixes(out, global_batch)
         return out
+
+    def step_e2e_uint8():
+        # SURVEY §8f.2 variant: the host hands over the resized uint8 frame (4x fewer H2D bytes); ToTensor + both
+        # Normalizes run in one device kernel.  Reported next to `e2e`, never instead of it.
+        out = enc.forward_uint8(frames_host.to(device, non_blocking=True))
+        if args.gather and distributed:
+            out = gather_prefixes(out, global_batch)
+        return out.float().mean(dim=(1, 2)).cpu()
 
     def step_e2e():
         px = {k: v.to(device, non_blocking=True) for k, v in px_host.items()}
@@ -246,6 +267,7 @@ def run_gpu(args) -> None:
     e2e_value = global_batch / (e2e_ms * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in px_host.values())
     d2h = B * 4
+    e2e_u8_ms = timed(step_e2e_uint8, e2e_steps, 1) / e2e_steps
 
     # ---- roofline of the dominant kernel (instrumented pass, not the headline number) ------------------------
     roof = None
@@ -258,16 +280,39 @@ def run_gpu(args) -> None:
             enc(px_dev)              # rank-local on purpose: no collective inside a rank-0-only block
         torch.cuda.synchronize()
         cats = ops.timing_collect()
+        recs = ops.timing_records(8192)
         ops.timing_enable(False)
         ops.timing_reset()
         g = cats["gemm"]
-        achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+        family = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         step_tflops = fused_flops_per_image() * B / (ms_per_step * 1e-3) / 1e12
+        # dominant kernel = the GEMM shape with the largest share of the step; its per-launch numbers
+        shapes = {}
+        for r in recs:
+            if r["cat"] != "gemm":
+                continue
+            key = (r["mode"], r["N"], r["K"], r["ln_folded"], r["emits_stats"])
+            a = shapes.setdefault(key, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += r["ms"]
+            a[2] += r["work"]
+        top = max(shapes.items(), key=lambda kv: kv[1][1])
+        (mode, Nn, Kk, lnf, st), (cnt, tms, twork) = top
+        mode_name = {0: "bias", 1: "bias+GELU", 2: "LayerScale+residual", 3: "patch"}[mode]
+        achieved = twork / (tms * 1e-3) / 1e12
         roof = {
-            "bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all shapes of the step)",
+            "bound": "tensor",
+            "kernel": f"gemm_bf16_kernel tcgen05 cta_group::2, epilogue {mode_name}"
+                      f"{' + folded LayerNorm' if lnf else ''}{' + stats/bf16-copy' if st else ''}, "
+                      f"M={int(round(twork / cnt / (2.0 * Nn * Kk)))} N={Nn} K={Kk}",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
+            "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+            "flops_per_launch": twork / cnt, "avg_launch_us": 1e3 * tms / cnt, "launches_per_step": cnt // 2,
+            "share_of_step": (tms / 2) / ms_per_step,
+            "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((mode, Nn, Kk, lnf, st)),
+            "traffic_source": "profiles/r01_ncu_full_c_kernels.md (ncu --set full, dram__bytes_read+write per launch)",
+            "gemm_family": {"achieved": family, "frac": family / peak, "note": "all tcgen05 GEMM launches of the step"},
             "gemm_ms_per_step": g["ms"] / 2, "gemm_launches_per_step": g["launches"] // 2,
             "whole_step": {"achieved": step_tflops, "frac_of_sustained": step_tflops / peak,
                            "frac_of_burst": step_tflops / float(peaks["bf16_tflops"]),
@@ -298,6 +343,10 @@ def run_gpu(args) -> None:
                                 "exceeds the 126 MB L2",
                        "collective": "nccl all-gather of prefixes" if (args.gather and distributed) else "none"},
             "clocks": clocks,
+            "e2e_uint8": {"value": global_batch / (e2e_u8_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_u8_ms,
+                          "h2d_bytes_per_step": frames_host.numel(), "d2h_bytes_per_step": d2h,
+                          "note": "extra (SURVEY 8f.2): resized uint8 HWC frames from pinned host memory; ToTensor + "
+                                  "both Normalizes in one device kernel (bit-identical to the host transform)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches_per_step) * args.steps,

@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["BLB_LIB"]) if os.environ.get("BLB_LIB") else PKG_DIR / "libbridgelang_b200.so"
 
 EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3
-DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_F16, DTYPE_F64 = 0, 1, 2, 3
 
 c_f32p = C.POINTER(C.c_float)
 
@@ -86,6 +86,12 @@ _SIGNATURES = {
     "blb_fused_featurize_project_forward": (C.c_int, [C.POINTER(VitWeights), C.POINTER(VitWeights),
                                                       C.POINTER(ProjectorWeights), C.c_void_p, C.c_void_p, C.c_int,
                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "blb_preprocess_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "blb_encode_actions": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
+    "blb_action_token_metrics": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int,
+                                           C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "blb_argmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "blb_detokenize_unnormalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

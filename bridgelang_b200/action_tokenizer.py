@@ -3,8 +3,9 @@
 Same constructor, attributes (`bins`, `bin_centers`, `action_token_begin_idx`, `n_bins`, `vocab_size`) and call
 signatures.  `decode_token_ids_to_actions` keeps the reference's NumPy-in / NumPy-out contract but the arithmetic
 (id → bin → centre, clip semantics included) runs in the CUDA kernel of csrc/decode_tail.cu and is bit-identical in
-float64; `decode_on_device` is the no-copy variant `predict_action` uses.  The encode path (`__call__`,
-np.digitize + tokenizer.decode to a string) is host-side text processing exactly as in the reference.
+float64; `decode_on_device` is the no-copy variant `predict_action` uses.  `__call__` (np.digitize + tokenizer.decode
+to a string) is host-side text processing exactly as in the reference; `encode_on_device` gives its token ids on the
+GPU and `action_metrics` the training loops' accuracy / L1.
 """
 
 from __future__ import annotations
@@ -51,6 +52,23 @@ class ActionTokenizer:
         """int64 CUDA ids [n] → (normalized, actions) float64 CUDA tensors; actions == normalized if stats is None."""
         t = self.tables(stats, device=action_token_ids.device)
         return ops.detokenize_unnormalize(action_token_ids.contiguous().view(-1), int(self.tokenizer.vocab_size), t)
+
+    # -- device encode / training metrics (SURVEY §8f.3-4) --------------------------------------------
+    def encode_on_device(self, action: torch.Tensor) -> torch.Tensor:
+        """`__call__` up to the token ids (clip → np.digitize → vocab_size − index) for a CUDA float32/float64 tensor of
+        any shape; the id → string step (`tokenizer.decode`) is text processing and stays on the host."""
+        if getattr(self, "_bins_dev", None) is None or self._bins_dev.device != action.device:
+            self._bins_dev = torch.from_numpy(np.ascontiguousarray(self.bins, dtype=np.float64)).to(action.device)
+        return ops.encode_actions(action, self._bins_dev, float(self.min_action), float(self.max_action),
+                                  int(self.tokenizer.vocab_size))
+
+    def action_metrics(self, logits: torch.Tensor, labels: torch.Tensor, num_patches: int):
+        """Action-token accuracy and L1 of the training loops (base_strategy.py:314-329, finetune.py:270-286) without the
+        `.cpu().numpy()` round trips.  Returns (accuracy float32 0-d, l1 float64 0-d) CUDA tensors."""
+        r = ops.action_token_metrics(logits, labels, num_patches, self.action_token_begin_idx,
+                                     int(self.tokenizer.vocab_size), self.tables(None, device=logits.device))
+        correct, n = r["counts"][0], r["counts"][1]
+        return correct.float() / n.float(), r["l1_sum"][0] / n.to(torch.float64)
 
     def decode_token_ids_to_actions(self, action_token_ids: np.ndarray) -> np.ndarray:
         ids_np = np.asarray(action_token_ids)

@@ -460,6 +460,25 @@ int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_v
   return 0;
 }
 
+int blb_preprocess_u8(const uint8_t* frames_hwc, int batch, const void* lut_bf16, void* out_dino_bf16,
+                      void* out_siglip_bf16, void* stream) {
+  return preprocess_u8(frames_hwc, batch, bf(lut_bf16), bf(out_dino_bf16), bf(out_siglip_bf16), as_stream(stream));
+}
+
+int blb_encode_actions(const void* actions, int dtype, int n, const double* bins, int n_bins, double min_action,
+                       double max_action, int vocab_size, int64_t* ids, void* stream) {
+  return encode_actions(actions, dtype, n, bins, n_bins, min_action, max_action, vocab_size, ids, as_stream(stream));
+}
+
+int blb_action_token_metrics(const void* logits, int dtype, int batch, int seq, int vocab, int64_t ld_row,
+                             int64_t ld_batch, int num_patches, const int64_t* labels, int64_t ld_labels,
+                             int action_token_begin_idx, int vocab_size, const double* bin_centers, int n_centers,
+                             int64_t* preds, double* absdiff, int64_t* counts, double* l1_sum, void* stream) {
+  return action_token_metrics(logits, dtype, batch, seq, vocab, ld_row, ld_batch, num_patches, labels, ld_labels,
+                              action_token_begin_idx, vocab_size, bin_centers, n_centers, preds, absdiff, counts, l1_sum,
+                              as_stream(stream));
+}
+
 int blb_argmax(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, void* stream) {
   return argmax_rows(logits, dtype, rows, vocab, ld, ids, as_stream(stream));
 }

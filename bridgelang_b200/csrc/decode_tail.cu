@@ -110,6 +110,128 @@ __global__ void detok_kernel(const int64_t* __restrict__ ids, int n, int vocab_s
   if (j < n) detok_one(ids[j], j, vocab_size, bin_centers, n_centers, action_dim, q01, q99, mask, norm_out, act_out);
 }
 
+// ---- ActionTokenizer.__call__, id part (action_tokenizer.py:38-47): clip → np.digitize(action, bins) → vocab_size − idx.
+// np.digitize with increasing bins returns #{bins <= x} (right=False); NaN sorts after every bin (→ n_bins), as np.clip
+// propagates NaN and NumPy orders NaN last.  float32 inputs are widened exactly, as NumPy's comparison does.
+template <typename T>
+__global__ void encode_kernel(const T* __restrict__ actions, int n, const double* __restrict__ bins, int n_bins,
+                              double lo, double hi, int vocab_size, int64_t* __restrict__ ids) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  T a = actions[j];
+  if (a < static_cast<T>(lo)) a = static_cast<T>(lo);   // np.clip in the array's own dtype
+  if (a > static_cast<T>(hi)) a = static_cast<T>(hi);
+  const double x = static_cast<double>(a);
+  int idx;
+  if (x != x) {
+    idx = n_bins;
+  } else {
+    int l = 0, r = n_bins;                              // first index with bins[i] > x
+    while (l < r) {
+      const int mid = (l + r) >> 1;
+      if (bins[mid] <= x) l = mid + 1; else r = mid;
+    }
+    idx = l;
+  }
+  ids[j] = static_cast<int64_t>(vocab_size) - idx;
+}
+
+int encode_actions(const void* actions, int dtype, int n, const double* bins, int n_bins, double lo, double hi,
+                   int vocab_size, int64_t* ids, cudaStream_t stream) {
+  if (actions == nullptr || bins == nullptr || ids == nullptr || n <= 0 || n_bins <= 0) return BLB_ERR_ARG;
+  const int blocks = (n + 127) / 128;
+  if (dtype == 0) encode_kernel<float><<<blocks, 128, 0, stream>>>(static_cast<const float*>(actions), n, bins, n_bins, lo, hi, vocab_size, ids);
+  else if (dtype == 3) encode_kernel<double><<<blocks, 128, 0, stream>>>(static_cast<const double*>(actions), n, bins, n_bins, lo, hi, vocab_size, ids);
+  else return BLB_ERR_ARG;
+  count_launch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ---- training-side action metrics (base_strategy.py:314-329, finetune.py:270-286) ---------------------------------
+//   preds = logits[:, P:-1].argmax(2);  gt = labels[:, 1:];  mask = gt > action_token_begin_idx
+//   accuracy = sum((preds == gt) & mask) / sum(mask);  l1 = mean |decode(preds[mask]) − decode(gt[mask])|
+// One block per (sample, position).  Positions whose label is not an action token never enter either metric, so
+// their 32064-wide argmax is skipped (pred = −1): with 7 action tokens per sample that is most of the rows.  The
+// per-position results are reduced by one block in a fixed order (deterministic; float64 sum).
+template <typename T>
+__global__ void __launch_bounds__(1024) action_metrics_rows_kernel(const T* __restrict__ logits, int vocab, long long ld_row,
+                                                                   long long ld_batch, int first_pos, int n_pos,
+                                                                   const int64_t* __restrict__ labels, long long ld_labels,
+                                                                   int begin_idx, int vocab_size,
+                                                                   const double* __restrict__ bin_centers, int n_centers,
+                                                                   int64_t* __restrict__ preds, double* __restrict__ absdiff) {
+  const int b = blockIdx.x / n_pos, p = blockIdx.x - b * n_pos;
+  const long long gt = labels[static_cast<size_t>(b) * ld_labels + 1 + p];
+  if (gt <= begin_idx) {                       // block-uniform
+    if (threadIdx.x == 0) { preds[blockIdx.x] = -1; absdiff[blockIdx.x] = 0.0; }
+    return;
+  }
+  const int best = block_argmax<T>(logits + static_cast<size_t>(b) * ld_batch + static_cast<size_t>(first_pos + p) * ld_row, vocab);
+  if (threadIdx.x == 0) {
+    preds[blockIdx.x] = best;
+    double a = 0.0, g = 0.0;
+    detok_one(best, 0, vocab_size, bin_centers, n_centers, 0, nullptr, nullptr, nullptr, &a, nullptr);
+    detok_one(gt, 0, vocab_size, bin_centers, n_centers, 0, nullptr, nullptr, nullptr, &g, nullptr);
+    absdiff[blockIdx.x] = fabs(__dsub_rn(a, g));
+  }
+}
+
+__global__ void __launch_bounds__(1024) action_metrics_reduce_kernel(const int64_t* __restrict__ preds,
+                                                                     const double* __restrict__ absdiff,
+                                                                     const int64_t* __restrict__ labels, long long ld_labels,
+                                                                     int batch, int n_pos, int begin_idx,
+                                                                     int64_t* __restrict__ counts, double* __restrict__ l1_sum) {
+  __shared__ long long s_c[1024], s_m[1024];
+  __shared__ double s_l[1024];
+  long long c = 0, m = 0;
+  double l = 0.0;
+  const int total = batch * n_pos;
+  for (int i = threadIdx.x; i < total; i += 1024) {      // fixed assignment + fixed tree → deterministic
+    const int b = i / n_pos, p = i - b * n_pos;
+    const long long gt = labels[static_cast<size_t>(b) * ld_labels + 1 + p];
+    if (gt > begin_idx) {
+      ++m;
+      c += preds[i] == gt;
+      l += absdiff[i];
+    }
+  }
+  s_c[threadIdx.x] = c; s_m[threadIdx.x] = m; s_l[threadIdx.x] = l;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_c[threadIdx.x] += s_c[threadIdx.x + o];
+      s_m[threadIdx.x] += s_m[threadIdx.x + o];
+      s_l[threadIdx.x] += s_l[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { counts[0] = s_c[0]; counts[1] = s_m[0]; *l1_sum = s_l[0]; }
+}
+
+int action_token_metrics(const void* logits, int dtype, int batch, int seq, int vocab, int64_t ld_row, int64_t ld_batch,
+                         int num_patches, const int64_t* labels, int64_t ld_labels, int begin_idx, int vocab_size,
+                         const double* bin_centers, int n_centers, int64_t* preds, double* absdiff, int64_t* counts,
+                         double* l1_sum, cudaStream_t stream) {
+  const int n_pos = seq - 1 - num_patches;     // logits[:, P:-1]
+  if (logits == nullptr || labels == nullptr || bin_centers == nullptr || preds == nullptr || absdiff == nullptr ||
+      counts == nullptr || l1_sum == nullptr || batch <= 0 || vocab <= 0 || n_pos <= 0 || n_centers <= 0)
+    return BLB_ERR_ARG;
+  const int blocks = batch * n_pos;
+#define BLB_AM(T) action_metrics_rows_kernel<T><<<blocks, 1024, 0, stream>>>(static_cast<const T*>(logits), vocab, ld_row, \
+      ld_batch, num_patches, n_pos, labels, ld_labels, begin_idx, vocab_size, bin_centers, n_centers, preds, absdiff)
+  switch (dtype) {
+    case 0: BLB_AM(float); break;
+    case 1: BLB_AM(__nv_bfloat16); break;
+    case 2: BLB_AM(__half); break;
+    default: return BLB_ERR_ARG;
+  }
+#undef BLB_AM
+  action_metrics_reduce_kernel<<<1, 1024, 0, stream>>>(preds, absdiff, labels, ld_labels, batch, n_pos, begin_idx, counts,
+                                                       l1_sum);
+  count_launch(2);
+  return static_cast<int>(cudaGetLastError());
+}
+
 int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int vocab_size,
                                   const double* bin_centers, int n_centers, int action_dim, const double* q01,
                                   const double* q99,

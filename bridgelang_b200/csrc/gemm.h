@@ -111,6 +111,8 @@ void attention_set_trace(long long* device_buffer);
 
 // patch_embed.cu — im2col for Conv2d(3, D, 14, stride 14) and the cls/reg prefix rows
 int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int ldk, cudaStream_t stream);
+int preprocess_u8(const uint8_t* frames, int B, const __nv_bfloat16* lut, __nv_bfloat16* out_dino,
+                  __nv_bfloat16* out_siglip, cudaStream_t stream);
 int write_prefix_tokens(const float* prefix, float* resid, int B, int T, int n_prefix, int D, cudaStream_t stream);
 
 // decode_tail.cu
@@ -123,5 +125,12 @@ int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int v
                                   const double* q99,
                                   const uint8_t* mask, int64_t* ids, double* norm_out, double* act_out,
                                   cudaStream_t stream);
+
+int encode_actions(const void* actions, int dtype, int n, const double* bins, int n_bins, double lo, double hi,
+                   int vocab_size, int64_t* ids, cudaStream_t stream);
+int action_token_metrics(const void* logits, int dtype, int batch, int seq, int vocab, int64_t ld_row, int64_t ld_batch,
+                         int num_patches, const int64_t* labels, int64_t ld_labels, int begin_idx, int vocab_size,
+                         const double* bin_centers, int n_centers, int64_t* preds, double* absdiff, int64_t* counts,
+                         double* l1_sum, cudaStream_t stream);
 
 }  // namespace blb

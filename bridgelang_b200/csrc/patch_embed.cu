@@ -48,6 +48,66 @@ int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int 
   return static_cast<int>(cudaGetLastError());
 }
 
+// ---- device-side image preprocessing -------------------------------------------------------------
+// One uint8 HWC frame feeds BOTH towers: ToTensor (x/255) + per-tower Normalize ((t-mean)/std) + the bf16 cast of
+// `.to(device, dtype=bf16)` (processing_prismatic.py:128-145, dinosiglip_vit.py:33-40, run_openvla_demo.py:38-41)
+// collapse to a 256-entry table per (tower, channel) — built on the host with the reference's own torch ops, so the
+// result is bit-identical by construction — and the kernel is a pure gather: 3 B read, 12 B written per pixel.
+// lut: bf16 [2 towers][3 channels][256].   frames: uint8 [B,224,224,3]   →   out_*: bf16 [B,3,224,224]
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ frames,
+                                                            const __nv_bfloat16* __restrict__ lut,
+                                                            __nv_bfloat16* __restrict__ out_dino,
+                                                            __nv_bfloat16* __restrict__ out_siglip, int B) {
+  __shared__ __nv_bfloat16 s_lut[2 * 3 * 256];
+  for (int i = threadIdx.x; i < 2 * 3 * 256; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  // one thread per 4 consecutive pixels of a row: 12 contiguous input bytes, 3 channels x 4 bf16 (8 B) out per tower
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * IMG * (IMG / 4);
+  if (idx >= total) return;
+  const int x4 = static_cast<int>(idx % (IMG / 4));
+  const long long rowi = idx / (IMG / 4);
+  const int y = static_cast<int>(rowi % IMG);
+  const int b = static_cast<int>(rowi / IMG);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(frames + ((static_cast<size_t>(b) * IMG + y) * IMG + x4 * 4) * 3);
+  const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+  uint8_t px[12];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    px[i] = (w0 >> (8 * i)) & 0xFF;
+    px[4 + i] = (w1 >> (8 * i)) & 0xFF;
+    px[8 + i] = (w2 >> (8 * i)) & 0xFF;
+  }
+#pragma unroll
+  for (int tower = 0; tower < 2; ++tower) {
+    __nv_bfloat16* out = tower == 0 ? out_dino : out_siglip;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const __nv_bfloat16* t = s_lut + (tower * 3 + c) * 256;
+      __nv_bfloat16 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = t[px[3 * i + c]];
+      uint2 pk;
+      pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(v[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(v[1])) << 16);
+      pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(v[2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(v[3])) << 16);
+      *reinterpret_cast<uint2*>(out + ((static_cast<size_t>(b) * 3 + c) * IMG + y) * IMG + x4 * 4) = pk;
+    }
+  }
+}
+
+int preprocess_u8(const uint8_t* frames, int B, const __nv_bfloat16* lut, __nv_bfloat16* out_dino,
+                  __nv_bfloat16* out_siglip, cudaStream_t stream) {
+  if (frames == nullptr || lut == nullptr || out_dino == nullptr || out_siglip == nullptr || B <= 0) return BLB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(frames) & 3) != 0 || (reinterpret_cast<uintptr_t>(out_dino) & 7) != 0 ||
+      (reinterpret_cast<uintptr_t>(out_siglip) & 7) != 0)
+    return BLB_ERR_ALIGN;
+  const long long total = static_cast<long long>(B) * IMG * (IMG / 4);
+  TimingScope ts(TIME_OTHER, 15.0 * B * IMG * IMG, stream);
+  preprocess_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(frames, lut, out_dino, out_siglip, B);
+  count_launch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
 __global__ void prefix_kernel(const float* __restrict__ prefix, float* __restrict__ resid, int T, int n_prefix,
                               int D) {
   const int b = blockIdx.x;

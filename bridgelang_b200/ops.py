@@ -183,6 +183,57 @@ def argmax_detokenize_unnormalize(logits: torch.Tensor, vocab_size: int, tables:
     return ids, norm, act
 
 
+def preprocess_u8(frames: torch.Tensor, lut: torch.Tensor):
+    """uint8 [B,224,224,3] CUDA frames → (dino, siglip) bf16 [B,3,224,224]; lut bf16 [2,3,256] (see vision.py)."""
+    _need_cuda(frames, lut)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and tuple(frames.shape[1:]) == (224, 224, 3)
+    assert lut.dtype == torch.bfloat16 and lut.is_contiguous() and tuple(lut.shape) == (2, 3, 256)
+    B = frames.shape[0]
+    dino = torch.empty((B, 3, 224, 224), dtype=torch.bfloat16, device=frames.device)
+    siglip = torch.empty_like(dino)
+    _lib.check(_lib.load().blb_preprocess_u8(frames.data_ptr(), B, lut.data_ptr(), dino.data_ptr(), siglip.data_ptr(),
+                                             _stream()), "preprocess_u8")
+    return dino, siglip
+
+
+def encode_actions(actions: torch.Tensor, bins: torch.Tensor, min_action: float, max_action: float,
+                   vocab_size: int) -> torch.Tensor:
+    """clip → np.digitize(bins) → vocab_size − index, on the device; actions float32/float64, any shape."""
+    _need_cuda(actions, bins)
+    assert actions.dtype in (torch.float32, torch.float64) and bins.dtype == torch.float64 and bins.is_contiguous()
+    a = actions.contiguous()
+    ids = torch.empty(a.shape, dtype=torch.int64, device=a.device)
+    if a.numel() == 0:
+        return ids
+    dt = _lib.DTYPE_F32 if a.dtype == torch.float32 else _lib.DTYPE_F64
+    _lib.check(_lib.load().blb_encode_actions(a.data_ptr(), dt, a.numel(), bins.data_ptr(), bins.numel(),
+                                              float(min_action), float(max_action), int(vocab_size), ids.data_ptr(),
+                                              _stream()), "encode_actions")
+    return ids
+
+
+def action_token_metrics(logits: torch.Tensor, labels: torch.Tensor, num_patches: int, action_token_begin_idx: int,
+                         vocab_size: int, tables: "DecodeTables"):
+    """base_strategy.py:314-329 on the device.  Returns dict(preds [B, L-1] (−1 where unmasked), counts int64 [2] =
+    (#correct, #mask), l1_sum float64 [1]); accuracy = counts[0]/counts[1], l1 = l1_sum/counts[1] (no host sync here)."""
+    _need_cuda(logits, labels)
+    assert logits.dim() == 3 and logits.stride(2) == 1 and logits.dtype in _DTYPES
+    assert labels.dim() == 2 and labels.dtype == torch.int64 and labels.stride(1) == 1
+    B, S, V = logits.shape
+    n_pos = S - 1 - num_patches
+    assert n_pos > 0 and labels.shape[0] == B and labels.shape[1] >= n_pos + 1
+    preds = torch.empty((B, n_pos), dtype=torch.int64, device=logits.device)
+    absdiff = torch.empty((B, n_pos), dtype=torch.float64, device=logits.device)
+    counts = torch.empty((2,), dtype=torch.int64, device=logits.device)
+    l1_sum = torch.empty((1,), dtype=torch.float64, device=logits.device)
+    _lib.check(_lib.load().blb_action_token_metrics(
+        logits.data_ptr(), _DTYPES[logits.dtype], B, S, V, logits.stride(1), logits.stride(0), num_patches,
+        labels.data_ptr(), labels.stride(0), int(action_token_begin_idx), int(vocab_size), tables.bin_centers.data_ptr(),
+        tables.bin_centers.numel(), preds.data_ptr(), absdiff.data_ptr(), counts.data_ptr(), l1_sum.data_ptr(),
+        _stream()), "action_token_metrics")
+    return {"preds": preds, "absdiff": absdiff, "counts": counts, "l1_sum": l1_sum}
+
+
 def launch_count() -> int:
     return int(_lib.load().blb_launch_count())
 

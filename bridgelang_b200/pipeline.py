@@ -67,6 +67,14 @@ class VisualPrefixEncoder(nn.Module):
             "fused_featurize_project_forward")
         return (out, feats) if return_features else out
 
+    @torch.no_grad()
+    def forward_uint8(self, frames: torch.Tensor, return_features: bool = False):
+        """Already-resized uint8 frames [B,224,224,3] on the GPU → projected prefix (device-side ToTensor + both
+        Normalizes), then exactly `forward`."""
+        if not isinstance(self.vision_backbone, DinoSigLIPViTBackbone):
+            raise ValueError("forward_uint8 needs the native DinoSigLIPViTBackbone (dict pixel_values)")
+        return self.forward(self.vision_backbone.preprocess_uint8(frames), return_features=return_features)
+
 
 # ----------------------------------------------------------------------------------------------------------
 # data-parallel sharding

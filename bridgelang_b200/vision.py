@@ -306,6 +306,19 @@ class DinoSigLIPImageTransform:
         return {"dino": self.dino_image_transform(img, **kwargs), "siglip": self.siglip_image_transform(img, **kwargs)}
 
 
+def make_preprocess_lut(device="cuda") -> torch.Tensor:
+    """bf16 [2 towers (dino, siglip), 3 channels, 256]: ToTensor (x/255) → Normalize ((t−mean)/std, fp32) → bf16 cast,
+    evaluated with the reference transform's own torch ops on every uint8 value (processing_prismatic.py:128-145,
+    dinosiglip_vit.py:33-40) — the table `blb_preprocess_u8` gathers from, hence bit-identical to the host path."""
+    v = torch.arange(256, dtype=torch.uint8).to(torch.float32).div(255)                       # ToTensor
+    rows = []
+    for mean, std in ((DINO_MEAN, DINO_STD), (SIGLIP_MEAN, SIGLIP_STD)):
+        m = torch.as_tensor(mean, dtype=torch.float32)[:, None]
+        sd = torch.as_tensor(std, dtype=torch.float32)[:, None]
+        rows.append(v[None, :].repeat(3, 1).sub_(m).div_(sd))                                 # Normalize
+    return torch.stack(rows).to(torch.bfloat16).to(device).contiguous()
+
+
 def _make_transform(strategy: str, size: int, mean, std, *, crop_resize: int):
     """What timm.data.create_transform(is_training=False) yields for these checkpoints (bicubic Resize →
     CenterCrop → ToTensor → Normalize), modified per `image_resize_strategy` as dinosiglip_vit.py:82-134 does."""
@@ -406,6 +419,14 @@ class DinoSigLIPViTBackbone(VisionBackbone):
         self.dino_featurizer.forward_into(dino_px, out, 0)
         self.siglip_featurizer.forward_into(siglip_px, out, self.dino_featurizer.embed_dim)
         return out
+
+    def preprocess_uint8(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """already-resized uint8 frames [B,224,224,3] (HWC, on the GPU) → the `pixel_values` dict in bf16,
+        one device kernel for both towers instead of two host-side ToTensor+Normalize passes and a 4x larger H2D copy."""
+        if getattr(self, "_lut", None) is None or self._lut.device != frames.device:
+            self._lut = make_preprocess_lut(frames.device)
+        dino, siglip = ops.preprocess_u8(frames, self._lut)
+        return {"dino": dino, "siglip": siglip}
 
     @property
     def default_image_resolution(self) -> Tuple[int, int, int]:

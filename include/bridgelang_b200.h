@@ -180,6 +180,29 @@ int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_v
                                         void* projected_bf16, void* workspace, size_t workspace_bytes,
                                         void* stream);
 
+/* ---- rows SURVEY.md section 8f marks "next": the data formats either side of the path ------------------------------ */
+/* Image preprocessing on the device: one uint8 HWC frame [batch,224,224,3] -> both towers' normalized bf16
+ * [batch,3,224,224] tensors.  Replaces ToTensor + Normalize of DinoSigLIPImageTransform / PrismaticImageProcessor
+ * (dinosiglip_vit.py:33-40, processing_prismatic.py:128-145) and the .to(bf16) of the callers; lut_bf16 is
+ * [2 towers (dino, siglip)][3 channels][256] = the reference transform evaluated on every uint8 value (host-built,
+ * hence bit-identical).  Resizing stays on the host (PIL bicubic, upstream of the path). */
+int blb_preprocess_u8(const uint8_t* frames_hwc, int batch, const void* lut_bf16, void* out_dino_bf16,
+                      void* out_siglip_bf16, void* stream);
+/* ActionTokenizer.__call__ up to the token ids (action_tokenizer.py:38-47): clip, np.digitize(action, bins),
+ * vocab_size - index.  actions: BLB_DTYPE_F32 or BLB_DTYPE_F64 [n]; bins: float64 [n_bins] increasing. */
+#define BLB_DTYPE_F64 3
+int blb_encode_actions(const void* actions, int dtype, int n, const double* bins, int n_bins, double min_action,
+                       double max_action, int vocab_size, int64_t* ids, void* stream);
+/* Training-side action metrics (training/strategies/base_strategy.py:314-329, vla-scripts/finetune.py:270-286):
+ * preds = logits[:, num_patches:-1].argmax(2); gt = labels[:, 1:]; mask = gt > action_token_begin_idx.
+ * logits [batch, seq, vocab] with strides (ld_batch, ld_row, 1); labels int64 [batch, >= seq - num_patches], pitch ld_labels.
+ * Outputs: preds int64 [batch*(seq-1-num_patches)] (-1 where mask is false: those rows are not reduced at all),
+ * absdiff float64 same shape, counts[0] = #correct&mask, counts[1] = #mask, l1_sum = sum |decode(pred) - decode(gt)|. */
+int blb_action_token_metrics(const void* logits, int dtype, int batch, int seq, int vocab, int64_t ld_row,
+                             int64_t ld_batch, int num_patches, const int64_t* labels, int64_t ld_labels,
+                             int action_token_begin_idx, int vocab_size, const double* bin_centers, int n_centers,
+                             int64_t* preds, double* absdiff, int64_t* counts, double* l1_sum, void* stream);
+
 /* ---- decode tail ---------------------------------------------------------------------------------------- */
 /* torch.argmax over each full logits row (first max wins; NaN maximal) -> int64 ids. */
 int blb_argmax(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, void* stream);

@@ -65,3 +65,20 @@ def decode_tail(logits: np.ndarray, vocab_size: int, stats: Optional[Dict]) -> D
     norm = decode_token_ids_to_actions(ids, vocab_size)
     act = unnormalize(norm, stats) if stats is not None else norm
     return {"ids": ids, "normalized": norm, "actions": act}
+
+
+def action_token_metrics(logits, labels, num_patches: int, vocab_size: int, n_bins: int = 256):
+    """prismatic/training/strategies/base_strategy.py:314-329 (== vla-scripts/finetune.py:270-286), torch on CPU.
+    logits [B, P+L, V] float tensor, labels int64 [B, L].  Returns (accuracy float32, l1 float64, preds, mask)."""
+    import torch
+
+    begin = action_token_begin_idx(vocab_size, n_bins)
+    action_preds = logits[:, num_patches:-1].argmax(dim=2)
+    action_gt = labels[:, 1:]
+    mask = action_gt > begin
+    correct_preds = (action_preds == action_gt) & mask
+    action_accuracy = correct_preds.sum().float() / mask.sum().float()
+    continuous_actions_pred = torch.tensor(decode_token_ids_to_actions(action_preds[mask].cpu().numpy(), vocab_size, n_bins))
+    continuous_actions_gt = torch.tensor(decode_token_ids_to_actions(action_gt[mask].cpu().numpy(), vocab_size, n_bins))
+    action_l1_loss = torch.nn.functional.l1_loss(continuous_actions_pred, continuous_actions_gt)
+    return action_accuracy, action_l1_loss, action_preds, mask

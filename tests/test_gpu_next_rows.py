@@ -1,0 +1,115 @@
+"""SURVEY.md §8f "next" rows on a B200: device-side image preprocessing, ActionTokenizer encode ids, and the training
+loops' action-token accuracy / L1 — each against the reference's own formulation (torchvision transforms, NumPy
+digitize via the oracle + golden vectors, the base_strategy.py:314-329 restatement)."""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import bridgelang_b200 as blb
+from bridgelang_b200.weights import DINO_MEAN, DINO_STD, SIGLIP_MEAN, SIGLIP_STD, normalize_frames, synthetic_frames
+from oracle import action_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+class _Tok:
+    vocab_size = 32000
+
+
+@pytest.fixture(scope="module")
+def at():
+    return blb.ActionTokenizer(_Tok())
+
+
+# ---- preprocessing -------------------------------------------------------------------------------------------------
+def test_preprocess_uint8_bit_identical_to_torchvision_transforms():
+    from PIL import Image
+    from torchvision import transforms as T
+
+    bb = blb.DinoSigLIPViTBackbone("dinosiglip-vit-so-224px", "resize-naive")
+    frames = synthetic_frames(5, seed=11)
+    frames[0] = 0
+    frames[1] = 255
+    frames[2, :, :, 0], frames[2, :, :, 1], frames[2, :, :, 2] = 17, 128, 254        # channel order must survive
+    got = bb.preprocess_uint8(frames.cuda())
+    assert got["dino"].dtype == torch.bfloat16 and got["dino"].shape == (5, 3, 224, 224)
+    # (1) the tensor formulation used everywhere else in this repo
+    want = normalize_frames(frames)
+    for k in ("dino", "siglip"):
+        assert torch.equal(got[k].cpu(), want[k].to(torch.bfloat16)), k
+    # (2) the reference's literal transform objects on PIL images (ToTensor + Normalize, processing_prismatic.py:128-145)
+    for name, mean, std in (("dino", DINO_MEAN, DINO_STD), ("siglip", SIGLIP_MEAN, SIGLIP_STD)):
+        tf = T.Compose([T.ToTensor(), T.Normalize(mean=torch.tensor(mean), std=torch.tensor(std))])
+        for i in (2, 3):
+            ref = tf(Image.fromarray(frames[i].numpy())).to(torch.bfloat16)
+            assert torch.equal(got[name][i].cpu(), ref), (name, i)
+
+
+def test_forward_uint8_equals_forward_on_host_normalized_frames():
+    from bridgelang_b200.config import DINOV2_L14_REG4, SIGLIP_SO400M_14
+    from bridgelang_b200.weights import make_projector_state_dict, make_vit_state_dict
+
+    bb = blb.DinoSigLIPViTBackbone("dinosiglip-vit-so-224px", "resize-naive")
+    bb.dino_featurizer = blb.VisionTransformer(DINOV2_L14_REG4.with_depth(3))
+    bb.siglip_featurizer = blb.VisionTransformer(SIGLIP_SO400M_14.with_depth(3))
+    bb.dino_featurizer.load_state_dict(make_vit_state_dict(DINOV2_L14_REG4.with_depth(3), seed=1))
+    bb.siglip_featurizer.load_state_dict(make_vit_state_dict(SIGLIP_SO400M_14.with_depth(3), seed=2))
+    proj = blb.FusedMLPProjector(2176, 4096)
+    proj.load_state_dict(make_projector_state_dict(seed=3))
+    enc = blb.VisualPrefixEncoder(bb, proj).cuda()
+    frames = synthetic_frames(3, seed=4)
+    a = enc.forward_uint8(frames.cuda())
+    b = enc({k: v.to(torch.bfloat16).cuda() for k, v in normalize_frames(frames).items()})
+    assert torch.equal(a, b)
+
+
+# ---- encode --------------------------------------------------------------------------------------------------------
+def test_encode_ids_golden_and_oracle(at, golden_dir):
+    g = json.loads((golden_dir / "action_tokenizer.json").read_text())
+    enc = g["encode"]
+    a = torch.tensor(enc["actions"], dtype=torch.float64, device="cuda")
+    assert at.encode_on_device(a).cpu().tolist() == enc["ids"]
+    rng = np.random.default_rng(0)
+    for dtype in (np.float64, np.float32):
+        x = rng.uniform(-1.3, 1.3, size=(64, 7)).astype(dtype)
+        x[0, :4] = [-1.0, 1.0, 0.0, np.nan]
+        x[1] = at.bins[100:107].astype(dtype)                  # exactly on bin edges (digitize is right-open)
+        x[2] = np.nextafter(at.bins[100:107], -np.inf).astype(dtype)
+        want = action_oracle.encode_actions_to_token_ids(x, 32000)
+        got = at.encode_on_device(torch.from_numpy(x).cuda())
+        assert got.shape == x.shape
+        assert np.array_equal(got.cpu().numpy(), want), dtype
+    # round trip through the device decode: |decode(encode(a)) - a| <= one bin width
+    a = torch.linspace(-1, 1, 1001, dtype=torch.float64, device="cuda")
+    norm, _ = at.decode_on_device(at.encode_on_device(a))
+    assert float((norm - a).abs().max()) <= 2.0 / 255 + 1e-12
+
+
+# ---- training-side metrics -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_action_token_metrics_match_the_training_loop(at, dtype):
+    B, P, L, V = 5, 256, 24, 32064
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(B, P + L, V, generator=g).to(dtype)
+    labels = torch.full((B, L), -100, dtype=torch.int64)                 # IGNORE_INDEX everywhere ...
+    for b in range(B):
+        start = 8 + b
+        labels[b, start:start + 7] = torch.randint(31744, 32000, (7,), generator=g)   # ... except 7 action tokens
+        labels[b, start + 7] = 2                                                       # EOS: not > begin_idx
+        for j in range(7):                                                             # make ~half the predictions right
+            pos = P + start + j - 1                                                    # logits position predicting label j
+            tok = int(labels[b, start + j]) if (b + j) % 2 == 0 else 31744 + (b * 7 + j) % 256
+            logits[b, pos, tok] = 50.0
+    labels[0, 3] = 31743                                                  # == begin_idx: excluded by the strict '>'
+    want_acc, want_l1, want_preds, want_mask = action_oracle.action_token_metrics(logits.float(), labels, P, 32000)
+    acc, l1 = at.action_metrics(logits.cuda(), labels.cuda(), P)
+    r = blb.ops.action_token_metrics(logits.cuda(), labels.cuda(), P, at.action_token_begin_idx, 32000, at.tables(None))
+    assert int(r["counts"][1]) == int(want_mask.sum()) == 35
+    assert int(r["counts"][0]) == int(((want_preds == labels[:, 1:]) & want_mask).sum())
+    assert torch.equal(r["preds"].cpu()[want_mask], want_preds[want_mask])           # ids bit-exact where they count
+    assert bool((r["preds"].cpu()[~want_mask] == -1).all())                           # skipped rows
+    assert acc.dtype == torch.float32 and float(acc) == float(want_acc)
+    assert l1.dtype == torch.float64 and abs(float(l1) - float(want_l1)) <= 1e-12

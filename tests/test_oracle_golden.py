@@ -64,3 +64,41 @@ def test_projector_matches_reference_module(golden_dir):
     sd = {k.replace("__", "."): torch.from_numpy(z[k]) for k in z.files if k not in ("x", "y")}
     y = vit_oracle.projector_forward(sd, torch.from_numpy(z["x"]))
     assert torch.equal(y, torch.from_numpy(z["y"]))
+
+
+def test_action_token_metrics_restatement_on_a_hand_computed_case():
+    """base_strategy.py:314-329: 2 samples, 3 patches, 5 text positions; vocab 40 with 8 bins → begin_idx = 31."""
+    import torch
+    P, L, V = 3, 5, 40
+    logits = torch.zeros(2, P + L, V)
+    labels = torch.tensor([[-100, 33, 39, 2, -100], [-100, -100, 32, 31, 36]])     # 31 == begin_idx → not an action token
+    # position P+j-1 predicts label j (labels[:, 1:] vs logits[:, P:-1])
+    logits[0, P + 0, 33] = 9.0          # correct
+    logits[0, P + 1, 38] = 9.0          # wrong: 38 vs 39 → adjacent bins
+    logits[1, P + 1, 32] = 9.0          # correct
+    logits[1, P + 3, 36] = 9.0          # correct
+    acc, l1, preds, mask = action_oracle.action_token_metrics(logits, labels, P, V, n_bins=8)
+    assert mask.tolist() == [[True, True, False, False], [False, True, False, True]]
+    assert float(acc) == 0.75
+    _, centers = action_oracle.make_bins(8)
+    want = abs(centers[min(max(V - 38 - 1, 0), 6)] - centers[min(max(V - 39 - 1, 0), 6)]) / 4
+    assert abs(float(l1) - want) < 1e-15
+
+
+def test_preprocess_lut_matches_torchvision_on_every_uint8_value():
+    """The table `blb_preprocess_u8` gathers from == ToTensor + Normalize + bf16 cast of the reference transform."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from torchvision import transforms as T
+
+    from bridgelang_b200.vision import make_preprocess_lut
+    from bridgelang_b200.weights import DINO_MEAN, DINO_STD, SIGLIP_MEAN, SIGLIP_STD
+
+    lut = make_preprocess_lut("cpu")
+    assert lut.shape == (2, 3, 256) and lut.dtype == torch.bfloat16
+    ramp = np.tile(np.arange(256, dtype=np.uint8)[None, :, None], (2, 1, 3))          # [2,256,3] HWC image
+    for t, (mean, std) in enumerate(((DINO_MEAN, DINO_STD), (SIGLIP_MEAN, SIGLIP_STD))):
+        tf = T.Compose([T.ToTensor(), T.Normalize(mean=torch.tensor(mean), std=torch.tensor(std))])
+        ref = tf(Image.fromarray(ramp)).to(torch.bfloat16)                            # [3,2,256]
+        assert torch.equal(lut[t], ref[:, 0, :])

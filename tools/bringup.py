@@ -32,6 +32,28 @@ def time_it(fn, iters=10, warmup=3):
     return s.elapsed_time(e) / iters
 
 
+def case_gemm_fold(ctas: int, M: int, N: int, K: int, mode: int):
+    """the LN-folded variants as the towers run them: mode 0/1 consume (stats, colsum), mode 2 emits (stats, xb)."""
+    ops.set_gemm_cta_group(ctas)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    if mode in (ops.EPI_BIAS, ops.EPI_BIAS_GELU):
+        _, st = ops.rowstats_cast(a.float(), ops.gemm_stats_parts(K))
+        cs = w.float().sum(dim=1)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: ops.gemm(a, w, mode, bias=bias, out=out, ln_stats=st, ln_colsum=cs)
+    else:
+        gamma = torch.full((N,), 1e-3, device="cuda")
+        resid = torch.zeros(M, N, device="cuda")
+        stats = torch.empty(ops.gemm_stats_parts(N), M, 2, device="cuda")
+        xb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        fn = lambda: ops.gemm(a, w, 2, bias=bias, gamma=gamma, resid=resid, stats_out=stats, xb_out=xb)
+    ms = time_it(fn)
+    print(f"gemm_fold ctas={ctas} M={M} N={N} K={K} mode={mode}  time {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
 def case_gemm(ctas: int, M: int, N: int, K: int, mode: int, check: bool = True):
     ops.set_gemm_cta_group(ctas)
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -107,7 +129,9 @@ def case_argmax():
 
 if __name__ == "__main__":
     case = sys.argv[1]
-    if case == "gemm":
+    if case == "gemm_fold":
+        case_gemm_fold(*map(int, sys.argv[2:7]))
+    elif case == "gemm":
         ctas, M, N, K, mode = map(int, sys.argv[2:7])
         case_gemm(ctas, M, N, K, mode, check=(M * N <= 70000 * 4400))
     else:

@@ -22,7 +22,8 @@ LIB_PATH = PKG_DIR / "libbridgelang_b200.so"
 SOURCES = ["gemm_tcgen05.cu", "layernorm.cu", "attention.cu", "attention_tc.cu", "patch_embed.cu", "decode_tail.cu", "capi.cu"]
 HEADERS = [CSRC / "ptx.cuh", CSRC / "gemm.h", PKG_DIR.parent / "include" / "bridgelang_b200.h"]
 
-NVCC_FLAGS = [
+# BLB_NVCC_EXTRA: extra nvcc flags for development builds (e.g. "-DBLB_ATTN_POLY_MASK=0"), part of the build digest
+NVCC_FLAGS = os.environ.get("BLB_NVCC_EXTRA", "").split() + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",

@@ -59,6 +59,8 @@ class VisualPrefixEncoder(nn.Module):
         fused_dim = dino.struct.dim + siglip.struct.dim
         feats = torch.empty((B, NUM_PATCHES, fused_dim), dtype=torch.bfloat16, device=dev)
         out = torch.empty((B, NUM_PATCHES, proj.out_dim), dtype=torch.bfloat16, device=dev)
+        if B == 0:
+            return (out, feats) if return_features else out
         need = lib.blb_fused_workspace_bytes(C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), B)
         ws = ops.shared_workspace(dev, need)
         _lib.check(lib.blb_fused_featurize_project_forward(

@@ -78,6 +78,8 @@ class _ProjectorBase(nn.Module):
         else:
             assert out.dtype == torch.bfloat16 and out.is_cuda and out.stride(-1) == 1
             ld_out = out.stride(-2)
+        if rows == 0:
+            return out
         need = lib.blb_projector_workspace_bytes(C.byref(s), rows)
         ws = ops.shared_workspace(x.device, need)
         _lib.check(lib.blb_projector_forward(C.byref(s), x2.data_ptr(), x2.stride(0), rows, out.data_ptr(), ld_out,

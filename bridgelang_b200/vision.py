@@ -168,6 +168,8 @@ class VisionTransformer(nn.Module):
         pk = self.packed()
         B = pixels.shape[0]
         px = _as_pixels(pixels)
+        if B == 0:                      # an empty shard (more ranks than images): nothing to launch
+            return
         need = lib.blb_vit_workspace_bytes(C.byref(pk.struct), B)
         ws = self.workspace(need)
         _lib.check(lib.blb_vit_tower_forward(C.byref(pk.struct), px.data_ptr(), B, out.data_ptr(), out.stride(-2),

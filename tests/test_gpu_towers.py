@@ -171,3 +171,20 @@ def test_single_tower_backbones():
     for cls, ident, dim in ((blb.SigLIPViTBackbone, "siglip-vit-so400m", 1152), (blb.DinoV2ViTBackbone, "dinov2-vit-l", 1024)):
         bb = cls(ident, "resize-naive")
         assert bb.embed_dim == dim and bb.num_patches == 256
+
+
+def test_edge_batches_empty_single_and_ragged(full_model):
+    """Empty shard (more ranks than images), a single image, and a batch whose row count (7·261 = 1827, 7·256 = 1792)
+    is not a multiple of the 256-row tile: each image must get exactly the rows it gets in any other batch."""
+    enc, *_ = full_model
+    px = {k: v.bfloat16().cuda() for k, v in _pixels(7, seed=9).items()}
+    full = enc(px)
+    assert full.shape == (7, 256, 4096) and bool(torch.isfinite(full.float()).all())
+    one = enc({k: v[3:4] for k, v in px.items()})
+    assert torch.equal(one, full[3:4])
+    empty = enc({k: v[:0] for k, v in px.items()})
+    assert empty.shape == (0, 256, 4096)
+    feats = enc.vision_backbone({k: v[:0] for k, v in px.items()})
+    assert feats.shape == (0, 256, 2176) and enc.projector(feats).shape == (0, 256, 4096)
+    lo, hi = blb.shard_bounds(3, 5, 8)                      # rank 5 of 8 with 3 images: empty shard
+    assert lo == hi

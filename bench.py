@@ -219,20 +219,28 @@ def run_gpu(args) -> None:
             out = gather_prefixes(out, global_batch)
         return out
 
+    def endless(x):
+        while True:
+            yield x
+
+    # public serving API: VisualPrefixEncoder.stream() double-buffers the H2D copy of batch i+1 under the encode of
+    # batch i; every step still copies its own full batch from pinned host memory and reads its own result back
+    e2e_stream = enc.stream(endless(px_host))
+    e2e_stream_u8 = enc.stream(endless(frames_host), uint8=True)
+
     def step_e2e_uint8():
         # SURVEY §8f.2 variant: the host hands over the resized uint8 frame (4x fewer H2D bytes); ToTensor + both
         # Normalizes run in one device kernel.  Reported next to `e2e`, never instead of it.
-        out = enc.forward_uint8(frames_host.to(device, non_blocking=True))
+        out = next(e2e_stream_u8)
         if args.gather and distributed:
             out = gather_prefixes(out, global_batch)
-        return out.float().mean(dim=(1, 2)).cpu()
+        return out.mean(dim=(1, 2), dtype=torch.float32).cpu()
 
     def step_e2e():
-        px = {k: v.to(device, non_blocking=True) for k, v in px_host.items()}
-        out = enc(px)
+        out = next(e2e_stream)
         if args.gather and distributed:
             out = gather_prefixes(out, global_batch)
-        digest = out.float().mean(dim=(1, 2))           # one fp32 per image
+        digest = out.mean(dim=(1, 2), dtype=torch.float32)   # one fp32 per image (fp32 accumulation, no 1 GB copy)
         return digest.cpu()                              # D2H read of the step's result
 
     def timed(fn, steps, warmup):

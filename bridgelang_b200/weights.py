@@ -112,5 +112,5 @@ def normalize_frames(frames_u8: torch.Tensor) -> Dict[str, torch.Tensor]:
     for name, mean, std in (("dino", DINO_MEAN, DINO_STD), ("siglip", SIGLIP_MEAN, SIGLIP_STD)):
         m = torch.tensor(mean, device=x.device).view(1, 3, 1, 1)
         s = torch.tensor(std, device=x.device).view(1, 3, 1, 1)
-        out[name] = (x - m) / s
+        out[name] = ((x - m) / s).contiguous()             # NCHW-contiguous, like torchvision's ToTensor output
     return out

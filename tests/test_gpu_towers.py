@@ -188,3 +188,22 @@ def test_edge_batches_empty_single_and_ragged(full_model):
     assert feats.shape == (0, 256, 2176) and enc.projector(feats).shape == (0, 256, 4096)
     lo, hi = blb.shard_bounds(3, 5, 8)                      # rank 5 of 8 with 3 images: empty shard
     assert lo == hi
+
+
+def test_stream_double_buffered_equals_per_batch_forward(full_model):
+    """VisualPrefixEncoder.stream(): H2D of batch i+1 overlaps the encode of batch i; results are those of forward()."""
+    enc, *_ = full_model
+    host = []
+    for seed in (21, 22, 23, 24):
+        px = {k: v.bfloat16().pin_memory() for k, v in _pixels(2, seed=seed).items()}
+        host.append(px)
+    want = [enc({k: v.cuda() for k, v in px.items()}) for px in host]
+    got = list(enc.stream(host))
+    assert len(got) == 4
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    frames = [synthetic_frames(2, seed=s).pin_memory() for s in (31, 32, 33)]
+    got8 = list(enc.stream(frames, uint8=True))
+    for g, f in zip(got8, frames):
+        assert torch.equal(g, enc.forward_uint8(f.cuda()))
+    assert list(enc.stream([])) == []

@@ -270,12 +270,12 @@ def run_gpu(args) -> None:
     value = global_batch / (ms_per_step * 1e-3)
 
     # ---- e2e: host frames → H2D → forward → D2H digest -------------------------------------------------------
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_ms = timed(step_e2e, e2e_steps, 1) / e2e_steps
+    e2e_steps = max(2, args.steps)
+    e2e_ms = timed(step_e2e, e2e_steps, 2) / e2e_steps
     e2e_value = global_batch / (e2e_ms * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in px_host.values())
     d2h = B * 4
-    e2e_u8_ms = timed(step_e2e_uint8, e2e_steps, 1) / e2e_steps
+    e2e_u8_ms = timed(step_e2e_uint8, max(2, min(args.steps, 5)), 2) / max(2, min(args.steps, 5))
 
     # ---- roofline of the dominant kernel (instrumented pass, not the headline number) ------------------------
     roof = None

@@ -335,9 +335,9 @@ def run_gpu(args) -> None:
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = cpu_reference_images_per_s(steps=5, warmup=1, images_per_step=1)
+        ips, ms, cores = cpu_reference_images_per_s(steps=20, warmup=2, images_per_step=1)
         cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "5 timed + 1 warm-up forwards of 1 image, fp32 oracle restatement incl. the wasted last "
+               "sample": "20 timed + 2 warm-up forwards of 1 image, fp32 oracle restatement incl. the wasted last "
                          "block of each tower (420.15 GFLOP/image)", "ms_per_image": ms}
 
     if rank == 0:

@@ -209,11 +209,11 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   const int smem = (2 * TKP + 64) * PITCH * 2;
   if (smem > 227 * 1024) return BLB_ERR_SHAPE;
   auto kern = attention_kernel<HD, HDP>;
-  static int configured_smem = 0;
-  if (smem > configured_smem) {
+  static int configured_smem[BLB_MAX_DEVICES] = {};   // the attribute is per device
+  if (smem > configured_smem[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured_smem = smem;
+    configured_smem[current_device()] = smem;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T - q_begin) * T * HD, stream);
@@ -405,11 +405,11 @@ static int launch_attention_tail(const __nv_bfloat16* qkv, __nv_bfloat16* out, i
                                  cudaStream_t stream, int reverse) {
   constexpr int KEYS_W = 16 * TAIL_MAXBLK;
   const int smem = (16 + TAIL_WARPS * 2 * KEYS_W) * TAIL_PITCH * 2 + TAIL_WARPS * 16 * (2 + 64) * 4;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[BLB_MAX_DEVICES] = {};
+  if (!configured[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[current_device()] = true;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(64.0f);
   TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T - q_begin) * T * 64, stream);

@@ -545,11 +545,11 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
   if (rc == 0) rc = make_qkv_map(&maps.kv_x, qkv, B, T, H, HD, 16, KMAIN, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != 0) return rc;
   auto kern = attention_tc_kernel<HD, KX>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[BLB_MAX_DEVICES] = {};   // the attribute is per device
+  if (!configured[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[current_device()] = true;
   }
   const int grid = std::min(num_sms(), B * H);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));

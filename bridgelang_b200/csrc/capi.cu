@@ -66,9 +66,10 @@ struct TowerOverlap {
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 TowerOverlap* tower_overlap_ctx() {
-  static TowerOverlap ctx[64];
+  // per host thread and device: two threads driving the same GPU must not share the fork/join events
+  static thread_local TowerOverlap ctx[BLB_MAX_DEVICES];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= BLB_MAX_DEVICES) return nullptr;
   TowerOverlap& c = ctx[dev];
   if (c.side == nullptr) {
     if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;

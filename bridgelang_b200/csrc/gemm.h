@@ -55,6 +55,8 @@ void gemm_set_cta_group(int ctas);
 int gemm_stats_parts(int N);   // number of (sum, sumsq) pairs per row an EPI_RESIDUAL launch with this N writes
 int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int num_sms();
+int current_device();   // cudaGetDevice, clamped to [0, BLB_MAX_DEVICES): index for per-device one-time setup flags
+constexpr int BLB_MAX_DEVICES = 64;
 bool pdl_enabled();   // launch kernels with cudaLaunchAttributeProgrammaticStreamSerialization (default on)
 
 // <<<>>> replacement that adds the PDL attribute; the kernel must call pdl_wait() before touching global data

@@ -624,6 +624,12 @@ int timing_records(int max_records, int* cat, long long* tag, double* ms, double
 long long launch_count() { return g_launches; }
 void count_launch(int n) { g_launches += n; }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= BLB_MAX_DEVICES) return 0;
+  return dev;
+}
+
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -638,11 +644,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
                   const GemmEpilogue& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, RTMA, (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU)>;
   auto kern = gemm_bf16_kernel<BN, CTAS, MODE, RTMA>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[BLB_MAX_DEVICES] = {};   // the attribute is per device
+  if (!configured[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
+    configured[current_device()] = true;
   }
   const int tile_m = BM * CTAS;
   const int tiles = ((M + tile_m - 1) / tile_m) * (N / BN);

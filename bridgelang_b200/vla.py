@@ -90,7 +90,7 @@ class OpenVLA(nn.Module):
         embeds[:, :1] = tok[:, :1]                                        # <BOS>
         embeds[:, 1 + NUM_PATCHES:] = tok[:, 1:]
         # visual prefix, written by fc3's epilogue at token offset 1 (prismatic.py:389-396 splice)
-        feats = self.vision_backbone(pixel_values)
+        feats = self.vision_backbone(pixel_values)      # dict (native backbone) or packed [1,6,224,224] (HF twin)
         self.projector.project(feats, out=embeds, tok_in=NUM_PATCHES, tok_out=embeds.shape[1], tok_shift=1)
         out = self.llm(inputs_embeds=embeds.to(tok.dtype), use_cache=True)
         ids: List[torch.Tensor] = []
@@ -138,6 +138,78 @@ class OpenVLA(nn.Module):
         return len(self.norm_stats[unnorm_key]["action"]["q01"])
 
     def get_action_stats(self, unnorm_key: Optional[str] = None) -> Dict:
+        unnorm_key = self._check_unnorm_key(self.norm_stats, unnorm_key)
+        return self.norm_stats[unnorm_key]["action"]
+
+
+class OpenVLAForActionPrediction(nn.Module):
+    """HF twin, prismatic/extern/hf/modeling_prismatic.py:492-562 — the class every script of the fork drives
+    (run_openvla_demo.py:37-44, vla-scripts/deploy.py:104-105, experiments/robot/openvla_utils.py:166-169):
+
+        inputs = processor(prompt, image).to(device, dtype=torch.bfloat16)
+        action = vla.predict_action(**inputs, unnorm_key="bridge_orig", do_sample=False)
+
+    Same call: `predict_action(input_ids, unnorm_key=None, **kwargs)` with `pixel_values` [1,6,224,224] (dino channels
+    first, processing_prismatic.py:143) among the kwargs; `attention_mask` / `do_sample=False` / `use_cache` are
+    accepted (greedy decoding is what the reference runs, modeling_prismatic.py:518 with do_sample=False).  Attributes
+    `norm_stats`, `bins`, `bin_centers`, `vocab_size` (= text vocab − pad_to_multiple_of, :504) as in the reference;
+    same assertion messages.  The visual prefix is computed once per action whatever `use_cache` says."""
+
+    def __init__(self, vision_backbone: nn.Module, projector: nn.Module, language_model: nn.Module,
+                 norm_stats: Dict[str, Dict[str, Any]], text_vocab_size: int = 32064, pad_to_multiple_of: int = 64,
+                 n_action_bins: int = 256) -> None:
+        super().__init__()
+        self.vision_backbone, self.projector, self.language_model = vision_backbone, projector, language_model
+        self.norm_stats = norm_stats
+        self.bins = np.linspace(-1, 1, n_action_bins)
+        self.bin_centers = (self.bins[:-1] + self.bins[1:]) / 2.0
+        self.vocab_size = text_vocab_size - pad_to_multiple_of
+
+        class _Vocab:                               # ActionTokenizer only needs `.vocab_size` for the decode path
+            vocab_size = self.vocab_size
+        self._action_tokenizer = ActionTokenizer(_Vocab(), bins=n_action_bins)
+        # shares the greedy loop with the native class; kept out of the module tree so that state_dict() has the
+        # reference's keys only (vision_backbone.*, projector.*, language_model.*)
+        object.__setattr__(self, "_core", OpenVLA(vision_backbone, projector, language_model, _Vocab(), norm_stats,
+                                                  self._action_tokenizer))
+
+    @torch.inference_mode()
+    def predict_action(self, input_ids: Optional[torch.LongTensor] = None, unnorm_key: Optional[str] = None,
+                       **kwargs: Any) -> np.ndarray:
+        pixel_values = kwargs.get("pixel_values")
+        if input_ids is None or pixel_values is None:
+            raise ValueError("predict_action needs `input_ids` and `pixel_values` (the processor's outputs)")
+        if kwargs.get("do_sample", False):
+            raise ValueError("the native decode tail is greedy (the reference calls generate with do_sample=False)")
+        if not torch.all(input_ids[:, -1] == 29871):                      # modeling_prismatic.py:512-515
+            input_ids = torch.cat(
+                (input_ids, torch.unsqueeze(torch.Tensor([29871]).long(), dim=0).to(input_ids.device)), dim=1)
+        action_dim = self.get_action_dim(unnorm_key)
+        ids = self._core.generate_action_token_ids(input_ids, pixel_values, action_dim)
+        _, actions = self._action_tokenizer.decode_on_device(ids, self.get_action_stats(unnorm_key))
+        return actions.cpu().numpy()
+
+    @staticmethod
+    def _check_unnorm_key(norm_stats: Dict[str, Dict[str, Any]], unnorm_key: Optional[str]) -> str:
+        if unnorm_key is None:
+            assert len(norm_stats) == 1, (
+                f"Your model was trained on more than one dataset, "
+                f"please pass a `unnorm_key` from the following options to choose the statistics "
+                f"used for un-normalizing actions: {norm_stats.keys()}"
+            )
+            unnorm_key = next(iter(norm_stats.keys()))
+
+        assert unnorm_key in norm_stats, (
+            f"The `unnorm_key` you chose is not in the set of available dataset statistics, "
+            f"please choose from: {norm_stats.keys()}"
+        )
+        return unnorm_key
+
+    def get_action_dim(self, unnorm_key: Optional[str] = None) -> int:
+        unnorm_key = self._check_unnorm_key(self.norm_stats, unnorm_key)
+        return len(self.norm_stats[unnorm_key]["action"]["q01"])
+
+    def get_action_stats(self, unnorm_key: Optional[str] = None) -> Dict[str, Any]:
         unnorm_key = self._check_unnorm_key(self.norm_stats, unnorm_key)
         return self.norm_stats[unnorm_key]["action"]
 

@@ -100,3 +100,32 @@ def test_unnorm_key_errors(vla):
     img = Image.fromarray(np.zeros((224, 224, 3), dtype=np.uint8))
     with pytest.raises(AssertionError, match="not in the set of available statistics"):
         vla.predict_action(img, "do something", unnorm_key="no_such_dataset")
+
+
+def test_hf_twin_predict_action_equals_native(vla):
+    """OpenVLAForActionPrediction.predict_action(input_ids, pixel_values=[1,6,224,224], unnorm_key, do_sample=False)
+    — the call of run_openvla_demo.py:37-44 / deploy.py:104-105 — on the same weights gives the native class's action."""
+    from PIL import Image
+    bb = blb.PrismaticVisionBackbone(True, [224, 224], [DINOV2_L14_REG4.timm_id, SIGLIP_SO400M_14.timm_id], [None, None])
+    bb.featurizer = blb.VisionTransformer(DINOV2_L14_REG4.with_depth(3), ls_param_name="scale_factor")
+    bb.fused_featurizer = blb.VisionTransformer(SIGLIP_SO400M_14.with_depth(3), ls_param_name="scale_factor")
+    bb.featurizer.load_state_dict(make_vit_state_dict(DINOV2_L14_REG4.with_depth(3), seed=1))      # timm's `gamma` accepted
+    bb.fused_featurizer.load_state_dict(make_vit_state_dict(SIGLIP_SO400M_14.with_depth(3), seed=2))
+    psd = make_projector_state_dict(seed=3)
+    proj = blb.PrismaticProjector(True, 2176, 4096)
+    proj.load_state_dict({f"fc{i + 1}.{p}": psd[f"projector.{2 * i}.{p}"] for i in range(3) for p in ("weight", "bias")})
+    bb.cuda(), proj.cuda()
+    twin = blb.OpenVLAForActionPrediction(bb, proj, vla.llm, STATS, text_vocab_size=32064, pad_to_multiple_of=64)
+    assert twin.vocab_size == 32000 and twin.bin_centers.shape == (255,)
+    assert not any(k.startswith("_core") for k in twin.state_dict())
+    rng = np.random.default_rng(0)
+    image = Image.fromarray((rng.random((256, 256, 3)) * 255).astype(np.uint8))
+    instruction = "Pick up the red block"
+    want = vla.predict_action(image, instruction, unnorm_key="bridge_orig")
+    px = vla.vision_backbone.get_image_transform()(image)
+    packed = torch.cat([px["dino"], px["siglip"]], dim=0)[None].to("cuda", dtype=torch.bfloat16)   # processing_prismatic.py:143
+    input_ids = vla._prepare_input_ids(instruction, torch.device("cuda"))[:, :-1]                  # without the 29871 token
+    got = twin.predict_action(input_ids=input_ids, pixel_values=packed, unnorm_key="bridge_orig", do_sample=False)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    with pytest.raises(AssertionError, match="not in the set of available dataset statistics"):
+        twin.predict_action(input_ids=input_ids, pixel_values=packed, unnorm_key="nope")

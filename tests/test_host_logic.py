@@ -155,6 +155,11 @@ def test_unnorm_key_checks_match_reference_messages():
     with pytest.raises(AssertionError, match="not in the set of available statistics"):
         blb.OpenVLA._check_unnorm_key(stats, "c")
     assert blb.OpenVLA._check_unnorm_key({"a": stats["a"]}, None) == "a"
+    # HF twin (modeling_prismatic.py:538-552): its own wording
+    with pytest.raises(AssertionError, match="trained on more than one dataset"):
+        blb.OpenVLAForActionPrediction._check_unnorm_key(stats, None)
+    with pytest.raises(AssertionError, match="not in the set of available dataset statistics"):
+        blb.OpenVLAForActionPrediction._check_unnorm_key(stats, "c")
 
 
 def test_prompt_builder_format():

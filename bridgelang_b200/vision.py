@@ -338,6 +338,114 @@ def _make_transform(strategy: str, size: int, mean, std, *, crop_resize: int):
     raise ValueError(f"Image Resize Strategy `{strategy}` is not supported!")
 
 
+def letterbox_pad_transform(image, padding_fill_value: Tuple[int, int, int]):
+    """processing_prismatic.py:22-28"""
+    import torchvision.transforms.functional as TVF
+    (w, h), max_wh = image.size, max(image.size)
+    horizontal_pad, vertical_pad = int((max_wh - w) / 2), int((max_wh - h) / 2)
+    padding = (horizontal_pad, vertical_pad, horizontal_pad, vertical_pad)
+    return TVF.pad(image, padding, fill=padding_fill_value, padding_mode="constant")
+
+
+class PrismaticImageProcessor:
+    """HF twin of the image transform, prismatic/extern/hf/processing_prismatic.py:31-170: same constructor arguments
+    and attributes (`tvf_resize_params`, `tvf_crop_params`, `tvf_normalize_params`, `tvf_do_letterbox`, ...), same
+    `apply_transform(img) -> [3·n_towers, H, W]` (towers channel-stacked, dino first) and `preprocess(images)`.
+    The reference derives the per-tower (Resize, CenterCrop, ToTensor, Normalize) parameters by parsing a transform
+    that timm builds; timm is not a dependency here, and the parsed result is fully determined by the constructor
+    arguments (crop_pct = 1.0 → Resize(size = input_size[-1], bicubic, antialias), CenterCrop(input_size[-2:])), so the
+    parameters are written down directly.  `preprocess_to_device` is the SURVEY §8f.2 fast path: one host resize to a
+    uint8 frame, H2D of 3 bytes per pixel, ToTensor + every tower's Normalize + bf16 cast in one device kernel."""
+
+    model_input_names = ["pixel_values"]
+
+    def __init__(self, use_fused_vision_backbone: bool = False, image_resize_strategy: str = "letterbox",
+                 input_sizes: Optional[List[Tuple[int, int, int]]] = None, interpolations: Optional[List[str]] = None,
+                 means: Optional[List[Tuple[float, float, float]]] = None,
+                 stds: Optional[List[Tuple[float, float, float]]] = None, **kwargs: str) -> None:
+        from torchvision.transforms import InterpolationMode
+        import torchvision.transforms.functional as TVF
+        self.use_fused_vision_backbone = use_fused_vision_backbone
+        self.image_resize_strategy = image_resize_strategy
+        input_sizes = [(3, 224, 224)] if input_sizes is None else input_sizes
+        means = [(0.5, 0.5, 0.5)] if means is None else means
+        stds = [(0.5, 0.5, 0.5)] if stds is None else stds
+        interpolations = ["bicubic"] * len(input_sizes) if interpolations is None else interpolations
+        self.input_sizes, self.interpolations, self.means, self.stds = input_sizes, interpolations, means, stds
+        self.tvf_resize_params, self.tvf_crop_params, self.tvf_normalize_params = [], [], []
+        self.tvf_do_letterbox, self.tvf_letterbox_fill = False, None
+        modes = {"bicubic": InterpolationMode.BICUBIC, "bilinear": InterpolationMode.BILINEAR,
+                 "nearest": InterpolationMode.NEAREST}
+        for idx in range(len(input_sizes)):
+            size = self.input_sizes[idx][-1]
+            self.tvf_resize_params.append({"size": size, "interpolation": TVF.pil_modes_mapping[modes[interpolations[idx]]],
+                                           "max_size": None, "antialias": True})
+            self.tvf_crop_params.append({"output_size": tuple(self.input_sizes[idx][-2:])})
+            self.tvf_normalize_params.append({"mean": torch.tensor(self.means[idx]).float().numpy().tolist(),
+                                              "std": torch.tensor(self.stds[idx]).float().numpy().tolist(),
+                                              "inplace": False})
+            self.tvf_do_letterbox, self.tvf_letterbox_fill = False, None
+            if self.image_resize_strategy == "resize-naive":
+                self.tvf_resize_params[idx]["size"] = (size, size)
+            elif self.image_resize_strategy == "letterbox":
+                self.tvf_do_letterbox, self.tvf_letterbox_fill = True, tuple([int(x * 255) for x in self.means[idx]])
+            elif self.image_resize_strategy == "resize-crop":
+                pass
+            else:
+                raise ValueError(f"Image resize strategy `{self.image_resize_strategy}` is not supported!")
+        self._lut = None
+
+    def _resized(self, img, idx: int):
+        import torchvision.transforms.functional as TVF
+        return TVF.center_crop(TVF.resize(img, **self.tvf_resize_params[idx]), **self.tvf_crop_params[idx])
+
+    def apply_transform(self, img) -> torch.Tensor:
+        """processing_prismatic.py:128-145"""
+        import torchvision.transforms.functional as TVF
+        if self.tvf_do_letterbox:
+            img = letterbox_pad_transform(img, self.tvf_letterbox_fill)
+        imgs_t = []
+        for idx in range(len(self.input_sizes)):
+            img_idx_t = TVF.to_tensor(self._resized(img, idx))
+            imgs_t.append(TVF.normalize(img_idx_t, **self.tvf_normalize_params[idx]))
+        return torch.vstack(imgs_t)
+
+    def preprocess(self, images, return_tensors: Optional[str] = None, **_: str) -> Dict[str, Any]:
+        """Returns {"pixel_values": ...} (a plain dict standing in for transformers' BatchFeature): float32 torch tensor
+        for return_tensors="pt", NumPy otherwise — as processing_prismatic.py:147-167."""
+        if not isinstance(images, list):
+            images = [images]
+        pixel_values = torch.stack([self.apply_transform(img.convert("RGB")) for img in images])
+        return {"pixel_values": pixel_values.float() if return_tensors == "pt" else pixel_values.float().numpy()}
+
+    def __call__(self, images, **kwargs):
+        return self.preprocess(images, **kwargs)
+
+    def preprocess_to_device(self, images, device="cuda") -> torch.Tensor:
+        """[B, 6, 224, 224] bf16 on the device, bit-identical to `preprocess(...)["pixel_values"].to(device, bf16)` for the
+        fused 224 px DINOv2 + SigLIP configuration (both towers resize identically, so one uint8 frame feeds both)."""
+        import numpy as np
+        if not (self.use_fused_vision_backbone and len(self.input_sizes) == 2
+                and all(tuple(sz) == (3, 224, 224) for sz in self.input_sizes)
+                and self.tvf_resize_params[0] == self.tvf_resize_params[1]
+                and [tuple(m) for m in self.means] == [tuple(DINO_MEAN), tuple(SIGLIP_MEAN)]
+                and [tuple(sd) for sd in self.stds] == [tuple(DINO_STD), tuple(SIGLIP_STD)]):
+            raise ValueError("preprocess_to_device covers the fused 224 px DINOv2 + SigLIP processor configuration")
+        if not isinstance(images, list):
+            images = [images]
+        frames = []
+        for img in images:
+            img = img.convert("RGB")
+            if self.tvf_do_letterbox:
+                img = letterbox_pad_transform(img, self.tvf_letterbox_fill)
+            frames.append(np.asarray(self._resized(img, 0), dtype=np.uint8))
+        u8 = torch.from_numpy(np.stack(frames)).pin_memory().to(device, non_blocking=True)
+        if self._lut is None or self._lut.device != u8.device:
+            self._lut = make_preprocess_lut(u8.device)
+        dino, siglip = ops.preprocess_u8(u8, self._lut)
+        return torch.cat([dino, siglip], dim=1)
+
+
 # ======================================================================================================
 # Reference-facing backbones
 # ======================================================================================================

@@ -113,3 +113,17 @@ def test_action_token_metrics_match_the_training_loop(at, dtype):
     assert bool((r["preds"].cpu()[~want_mask] == -1).all())                           # skipped rows
     assert acc.dtype == torch.float32 and float(acc) == float(want_acc)
     assert l1.dtype == torch.float64 and abs(float(l1) - float(want_l1)) <= 1e-12
+
+
+def test_hf_processor_device_path_bit_identical():
+    """PrismaticImageProcessor.preprocess_to_device (one uint8 frame + LUT kernel) == preprocess(...).to(cuda, bf16)."""
+    from PIL import Image
+    proc = blb.PrismaticImageProcessor(True, "resize-naive", [(3, 224, 224)] * 2, ["bicubic"] * 2,
+                                       [DINO_MEAN, SIGLIP_MEAN], [DINO_STD, SIGLIP_STD])
+    rng = np.random.default_rng(5)
+    imgs = [Image.fromarray((rng.random((256, 256, 3)) * 255).astype(np.uint8)),
+            Image.fromarray((rng.random((480, 640, 3)) * 255).astype(np.uint8))]
+    want = proc.preprocess(imgs, return_tensors="pt")["pixel_values"].to("cuda", dtype=torch.bfloat16)
+    got = proc.preprocess_to_device(imgs)
+    assert got.shape == (2, 6, 224, 224) and got.dtype == torch.bfloat16
+    assert torch.equal(got, want)

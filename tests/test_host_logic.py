@@ -212,3 +212,28 @@ def test_all_gather_of_prefixes_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_hf_image_processor_twin_matches_native_transform():
+    """PrismaticImageProcessor.apply_transform (processing_prismatic.py:128-145) == the native dict transform,
+    channel-stacked dino first; attributes parsed like the reference; unsupported strategy raises like the reference."""
+    import numpy as np
+    from PIL import Image
+    from bridgelang_b200.weights import DINO_MEAN, DINO_STD, SIGLIP_MEAN, SIGLIP_STD
+    img = Image.fromarray((np.random.default_rng(0).random((300, 260, 3)) * 255).astype(np.uint8))
+    for strategy in ("resize-naive", "resize-crop", "letterbox"):
+        proc = blb.PrismaticImageProcessor(True, strategy, [(3, 224, 224), (3, 224, 224)], ["bicubic", "bicubic"],
+                                           [DINO_MEAN, SIGLIP_MEAN], [DINO_STD, SIGLIP_STD])
+        t = proc.apply_transform(img)
+        assert t.shape == (6, 224, 224) and t.dtype == torch.float32
+        if strategy != "letterbox":      # (the HF twin's letterbox fill uses the LAST tower's mean, :118; native: per tower)
+            d = blb.DinoSigLIPViTBackbone("dinosiglip-vit-so-224px", strategy).get_image_transform()(img)
+            assert torch.equal(t[:3], d["dino"]) and torch.equal(t[3:], d["siglip"])
+    proc = blb.PrismaticImageProcessor(True, "resize-naive", [(3, 224, 224)] * 2, ["bicubic"] * 2,
+                                       [DINO_MEAN, SIGLIP_MEAN], [DINO_STD, SIGLIP_STD])
+    assert proc.tvf_resize_params[0]["size"] == (224, 224) and proc.tvf_crop_params[0] == {"output_size": (224, 224)}
+    out = proc([img, img], return_tensors="pt")["pixel_values"]
+    assert out.shape == (2, 6, 224, 224) and torch.equal(out[0], out[1])
+    assert isinstance(proc(img)["pixel_values"], np.ndarray)
+    with pytest.raises(ValueError, match="is not supported"):
+        blb.PrismaticImageProcessor(True, "stretch", [(3, 224, 224)] * 2, ["bicubic"] * 2)

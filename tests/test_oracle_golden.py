@@ -102,3 +102,27 @@ def test_preprocess_lut_matches_torchvision_on_every_uint8_value():
         tf = T.Compose([T.ToTensor(), T.Normalize(mean=torch.tensor(mean), std=torch.tensor(std))])
         ref = tf(Image.fromarray(ramp)).to(torch.bfloat16)                            # [3,2,256]
         assert torch.equal(lut[t], ref[:, 0, :])
+
+
+def test_tower_oracle_against_frozen_hf_outputs(golden_dir):
+    """oracle/vit_oracle.py vs tests/golden/hf_towers_depth3.npz: outputs of transformers' independent DINOv2-reg4 and
+    SigLIP implementations, frozen by tests/golden/make_hf_tower_golden.py (timm itself cannot be installed offline)."""
+    import numpy as np
+    import torch
+    from bridgelang_b200.config import DINOV2_L14_REG4, SIGLIP_SO400M_14
+    from bridgelang_b200.weights import make_vit_state_dict
+    from oracle import vit_oracle
+
+    g = np.load(golden_dir / "hf_towers_depth3.npz")
+    depth = int(g["depth"])
+    for name, cfg0 in (("dino", DINOV2_L14_REG4), ("siglip", SIGLIP_SO400M_14)):
+        cfg = cfg0.with_depth(depth)
+        sd = make_vit_state_dict(cfg, seed=int(g[f"{name}_weight_seed"]), init="stress")
+        x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(int(g[f"{name}_pixel_seed"])))
+        with torch.no_grad():
+            got = vit_oracle.vit_intermediate(sd, cfg, x)
+        ref = torch.from_numpy(g[f"{name}_slice"])
+        scale = ref.abs().max()
+        assert ((got[0, ::8, ::16] - ref).abs().max() / scale).item() < 2e-5, name
+        assert abs(got.double().sum().item() - float(g[f"{name}_sum"])) < 1e-4 * float(g[f"{name}_abs_sum"])
+        assert abs(got.double().abs().sum().item() / float(g[f"{name}_abs_sum"]) - 1) < 1e-5

@@ -237,3 +237,20 @@ def test_hf_image_processor_twin_matches_native_transform():
     assert isinstance(proc(img)["pixel_values"], np.ndarray)
     with pytest.raises(ValueError, match="is not supported"):
         blb.PrismaticImageProcessor(True, "stretch", [(3, 224, 224)] * 2, ["bicubic"] * 2)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement of the reference path on the host cores) must print one JSON line
+    with the keys the round driver reads; it never touches a GPU."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("images/sec DinoSigLIP-224px featurize+project")
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]

@@ -89,6 +89,17 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -111,18 +122,21 @@ struct AttnCfg {
   static constexpr int OFF_Q1 = OFF_Q0 + Q_BYTES;
   static constexpr int OFF_K = OFF_Q1 + Q_BYTES;                 // [2 unit parities]
   static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;             // [2 unit parities]
-  static constexpr int OFF_XCHG = OFF_V + 2 * KV_BYTES;          // row max [2][128] + row sums [2][2][128] (fp32)
-  static constexpr int OFF_OST = OFF_XCHG + 6 * QT * 4;          // per-warp [32 rows x 64 B] output staging chunks
-  static constexpr int OFF_BAR = OFF_OST + 8 * 2048;
+  static constexpr int OFF_XCHG = OFF_V + 2 * KV_BYTES;          // partial row maxima [2 tile parities][2 groups][128] (fp32)
+  static constexpr int OFF_OST = OFF_XCHG + 4 * QT * 4;          // per-warp [32 rows x 64 B] output staging chunks
+  static constexpr int OFF_ONES = OFF_OST + 8 * 2048;            // 512 B of bf16 1.0: the B operand of the row-sum MMAs
+  static constexpr int OFF_BAR = OFF_ONES + 512;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  // TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [P_COL, P_COL + (256+KX)/2) | O fp32 [O_COL, O_COL + HDP)
+  // TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [P_COL, P_COL + (256+KX)/2) | O fp32 [O_COL, O_COL + HDP) |
+  //               row sums [SUM_COL, SUM_COL + 16)  (P · ones: every column holds Σ_k P[row, k])
   static constexpr int S_COLS = KMAIN + KX;
   static constexpr int P_COL = S_COLS;
   static constexpr int P_COLS = S_COLS / 2;
   static constexpr int O_COL = P_COL + P_COLS;
+  static constexpr int SUM_COL = O_COL + HDP;
   static constexpr int NREG_S = 128 + KX / 2;                    // S columns one softmax thread keeps in registers
   static_assert(Q_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0 && KV_MAIN % 1024 == 0, "1 KB aligned blocks");
-  static_assert(O_COL + HDP <= 512, "TMEM budget");
+  static_assert(SUM_COL + 16 <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
@@ -146,18 +160,68 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int HD, int KX>
+// Compiler-level fence for registers filled by an asynchronous tcgen05.ld: placed right after tcgen05.wait::ld, it makes
+// every later use of the values depend on a statement that cannot move above the wait (emits no instruction).
+__device__ __forceinline__ void reg_fence16(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+__device__ __forceinline__ void reg_fence8(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
+
+// 3-input max (FMNMX3 on sm_100a): halves the instruction count of the row-max pass
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// named barrier over the 64 threads of one row quarter (softmax warps q and q+4): id 1 + q
+__device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
+
+#ifndef BLB_ATTN_EPI_MODE
+#define BLB_ATTN_EPI_MODE 0
+#endif
+#ifndef BLB_ATTN_PCH
+#define BLB_ATTN_PCH 2
+#endif
+constexpr int PCH = BLB_ATTN_PCH;   // P / PV chunks per tile: 128/PCH keys of each group per chunk (4 or 2)
+static_assert(PCH == 4 || PCH == 2, "PCH");
+
+// 2^t for t <= 0 on the FMA pipe (the MUFU pipe, 16 results/clk/SM, is this kernel's ceiling): t = n + f with
+// n = round(t) taken from the low mantissa bits of t + 1.5·2^23 and f in [-0.5, 0.5]; degree-3 minimax fit of 2^f
+// (relative error 7.5e-5 = 1/26 of the bf16 half-ulp that P is rounded to), exponent added with one integer op.
+#ifndef BLB_ATTN_POLY_MASK
+#define BLB_ATTN_POLY_MASK 0   // bit i set: element i of every group of four uses exp2_poly instead of MUFU.EX2
+                               // (measured round 2: 8 → -3 %; the softmax warps are short of issue slots, not of MUFU)
+#endif
+__device__ __forceinline__ float exp2_poly(float t) {
+  t = fmaxf(t, -126.0f);
+  const float r = t + 12582912.0f;
+  const float f = t - (r - 12582912.0f);
+  float p = 0.0551716685f;
+  p = fmaf(p, f, 0.242611125f);
+  p = fmaf(p, f, 0.693260968f);
+  p = fmaf(p, f, 0.999928057f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+
+template <int HD, int KX, bool TRACE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out, int B, int T, int H,
                     float scale_log2, long long* trace, int reverse) {
-  // trace (debug only, normally nullptr): CTA 0 records clock64() at pipeline events of tiles [8, 16):
-  // trace[(g-8)*16 + e]; e: 0 mma:s_free(g) seen, 1 mma:S(g+1) issued, 2 mma:p_full(g)+o_empty seen, 3 mma:PV(g) issued,
-  //   8 sm:s_full seen, 9 sm:S in registers (s_free), 10 sm:max exchanged, 11 sm:p_empty seen, 12 sm:P stored/p_full,
-  //   13 sm:epilogue o_full seen, 14 sm:epilogue done
+  // trace (debug only, TRACE instantiation): every warp of CTA 0 records clock64() at pipeline events of tiles [8, 16):
+  // trace[((g-8)*12 + warp)*16 + e]; MMA warp e: 0 s_free(g) seen, 1 S(g+1) issued, 2 o_empty seen, 3 PV(g) issued,
+  //   4+c p_full[c](g) seen;  softmax warps e: 8 s_full seen, 9 S in registers (s_free), 10 max exchanged,
+  //   4+c P chunk c stored, 12 last P chunk published, 13 O(g-1) in registers, 14 epilogue(g-1) stores issued
 #define BLB_TRACE(g_, e_)                                                                   \
   do {                                                                                      \
-    if (trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (g_) >= 8 && (g_) < 16)            \
-      trace[((g_) - 8) * 16 + (e_)] = clock64();                                                                \
+    if (TRACE && trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (g_) >= 8 && (g_) < 16)   \
+      trace[(((g_) - 8) * 12 + (threadIdx.x >> 5)) * 16 + (e_)] = clock64();                                  \
   } while (0)
   using Cfg = AttnCfg<HD, KX>;
   extern __shared__ uint8_t smem_raw_attn[];
@@ -171,11 +235,11 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
   uint64_t* v_empty = bars + 10;   // [2]
   uint64_t* s_full = bars + 12;    // MMA → softmax: S(g) is in TMEM
   uint64_t* s_free = bars + 13;    // softmax → MMA: S(g) is in registers, TMEM columns reusable
-  uint64_t* p_full = bars + 14;    // softmax → MMA: P(g) is in TMEM
-  uint64_t* p_empty = bars + 15;   // MMA → softmax: PV(g) has consumed P(g)
-  uint64_t* o_full = bars + 16;    // MMA → epilogue
-  uint64_t* o_empty = bars + 17;   // epilogue → MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* o_full = bars + 14;    // MMA → epilogue: every PV chunk of tile g has retired
+  uint64_t* o_empty = bars + 15;   // epilogue → MMA: O(g) is in registers
+  uint64_t* p_full = bars + 16;    // [PCH] softmax → MMA: P chunk c of tile g is in TMEM
+  uint64_t* p_empty = bars + 16 + PCH;   // [PCH] MMA → softmax: PV chunk c of tile g has consumed its P columns
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * PCH);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int W_TMA = 8, W_MMA = 9, W_ALLOC = 10;
@@ -195,11 +259,16 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(p_full, 8); mbar_init(p_empty, 1);
+    mbar_init(s_full, 1); mbar_init(s_free, 8);
     mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    for (int c = 0; c < PCH; ++c) { mbar_init(&p_full[c], 8); mbar_init(&p_empty[c], 1); }
     fence_mbar_init();
   }
   if (warp == W_ALLOC) tmem_alloc<1>(tmem_slot, 512);
+  if (warp == 0) {           // 512 B of bf16 1.0 (layout-invariant: every element is one) → read by the async proxy (UMMA)
+    reinterpret_cast<uint4*>(smem + Cfg::OFF_ONES)[lane] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -263,8 +332,10 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         auto issue_s = [&](int g) {
           const int t = g & 1, i = g >> 1, kb = i & 1;
           if (t == 0) mbar_wait(&k_full[kb], static_cast<uint32_t>((i >> 1) & 1));
+          BLB_TRACE(g - 1, 8);
           mbar_wait(&q_full[t], static_cast<uint32_t>(i & 1));
           tc_fence_after();
+          BLB_TRACE(g - 1, 9);
           if (elect_one()) {
             const uint32_t qa = smem_u32(sQ[t]), ka = smem_u32(sK[kb]);
 #pragma unroll
@@ -297,30 +368,50 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
             BLB_TRACE(g, 1);
           }
           // ---------------- O(g) = P(g) · V   (A = P in TMEM, B = V as an MN-major smem operand) ----------------
+          // issued chunk by chunk as the softmax warps publish P: chunk c = keys [32c, 32c+32) of group 0 and
+          // [128+32c, 128+32c+32) of group 1 (+ the 16-key tail block with the last chunk), so that only the last
+          // chunk's MMAs are left when the tile's exp2 stream ends
           const int t = g & 1, i = g >> 1, kb = i & 1;
-          mbar_wait(p_full, static_cast<uint32_t>(g & 1));
+          const uint32_t ph = static_cast<uint32_t>(g & 1);
           if (t == 0) mbar_wait(&v_full[kb], static_cast<uint32_t>((i >> 1) & 1));
-          mbar_wait(o_empty, static_cast<uint32_t>(g & 1) ^ 1u);   // epilogue(g-1) drained the O accumulator
-          tc_fence_after();
+          mbar_wait(o_empty, ph ^ 1u);   // epilogue(g-1) holds O(g-1) in registers
           BLB_TRACE(g, 2);
-          if (elect_one()) {
-            const uint32_t o_col = tmem_base + Cfg::O_COL;
-            const uint32_t p_col = tmem_base + Cfg::P_COL;
-            const uint32_t va = smem_u32(sV[kb]);
+          const uint32_t o_col = tmem_base + Cfg::O_COL;
+          const uint32_t p_col = tmem_base + Cfg::P_COL;
+          const uint32_t sum_col = tmem_base + Cfg::SUM_COL;
+          const uint32_t va = smem_u32(sV[kb]);
+          const uint64_t ones = make_desc(smem_u32(smem + Cfg::OFF_ONES), 256, 6);   // [16 keys x 16] of 1.0
+#pragma unroll 1
+          for (int c = 0; c < PCH; ++c) {
+            mbar_wait(&p_full[c], ph);
+            tc_fence_after();
+            BLB_TRACE(g, 4 + c);
+            if (elect_one()) {
+              constexpr int MPG = 8 / PCH;         // 16-key MMAs per group and chunk
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {   // 16 keys per step: 8 packed P columns, V rows 16j..16j+15
-              umma_bf16_ts(o_col, p_col + j * 8, make_desc(va + j * 2048, 1024, 2), idesc_o_main, j > 0 ? 1u : 0u);
-              if (Cfg::SPLIT_D)
-                umma_bf16_ts(o_col + 64, p_col + j * 8,
-                             make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6), idesc_o_x, j > 0 ? 1u : 0u);
+              for (int jj = 0; jj < 2 * MPG; ++jj) {   // 16 keys per MMA: 8 packed P columns, V rows 16j..16j+15
+                const int j = (jj / MPG) * 8 + MPG * c + (jj % MPG);
+                umma_bf16_ts(o_col, p_col + j * 8, make_desc(va + j * 2048, 1024, 2), idesc_o_main,
+                             (c | jj) != 0 ? 1u : 0u);
+                if (Cfg::SPLIT_D)
+                  umma_bf16_ts(o_col + 64, p_col + j * 8,
+                               make_desc(va + Cfg::KV_MAIN + Cfg::KV_TAIL + j * 512, 256, 6), idesc_o_x,
+                               (c | jj) != 0 ? 1u : 0u);
+                // row sums on the tensor pipe: Σ_k P[row, k] · 1 (of the bf16-rounded P, i.e. exactly what PV uses)
+                umma_bf16_ts(sum_col, p_col + j * 8, ones, idesc_o_x, (c | jj) != 0 ? 1u : 0u);
+              }
+              if (KX > 0 && c == PCH - 1) {
+                umma_bf16_ts(o_col, p_col + 128, make_desc(va + Cfg::KV_MAIN, 1024, 2), idesc_o_main, 1u);
+                umma_bf16_ts(sum_col, p_col + 128, ones, idesc_o_x, 1u);
+              }
+              umma_commit<1>(&p_empty[c]);
+              if (c == PCH - 1) {
+                umma_commit<1>(o_full);
+                if (t == 1) umma_commit<1>(&v_empty[kb]);
+              }
             }
-            if (KX > 0)
-              umma_bf16_ts(o_col, p_col + 128, make_desc(va + Cfg::KV_MAIN, 1024, 2), idesc_o_main, 1u);
-            umma_commit<1>(p_empty);
-            umma_commit<1>(o_full);
-            if (t == 1) umma_commit<1>(&v_empty[kb]);
+            __syncwarp();
           }
-          __syncwarp();
           BLB_TRACE(g, 3);
         }
       }
@@ -335,74 +426,83 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int D = H * HD;
-    float* xmax = reinterpret_cast<float*>(smem + Cfg::OFF_XCHG);            // [2 groups][128 rows]
-    float* xsum = xmax + 2 * QT;                                             // [2 tile parities][2 groups][128]
-    float sum_prev = 0.f;
+    float* xmax = reinterpret_cast<float*>(smem + Cfg::OFF_XCHG);            // [2 tile parities][2 groups][128 rows]
     const int col_base = wg * 128;
     const int tail_key0 = KMAIN + wg * 8;                // first key of this group's 8 tail columns
+    const uint32_t ob = smem_u32(smem + Cfg::OFF_OST) + warp * 2048;         // this warp's output staging chunk
 
-    auto epilogue = [&](int gp, float own_sum) {
-      const int t = gp & 1, i = gp >> 1;
-      const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
-      const int u = reverse ? n_units - 1 - u_i : u_i;
-      const int b = u / H, h = u - b * H;
-      const float inv = 1.0f / (own_sum + xsum[(gp & 1) * 2 * QT + (wg ^ 1) * QT + row]);
+    // The epilogue of tile g-1 is split into three pieces that are threaded through the exp2 stream of tile g (the
+    // MUFU pipe is this kernel's bottleneck; everything else should issue while it is busy):
+    //   epi_load   O(g-1) → registers (the accumulator is then free for PV(g));  epi_stage  scale by 1/rowsum, round,
+    //   stage in smem;  epi_store  transposed read + coalesced global stores (8 rows x 64 contiguous bytes each)
+    uint32_t o_r[32];
+    uint32_t o_rx[Cfg::SPLIT_D ? 16 : 1];
+    uint32_t o_sum = 0;
+    auto epi_load = [&](int gp) {
       mbar_wait(o_full, static_cast<uint32_t>(gp & 1));
       tc_fence_after();
-      if (warp == 0 && lane == 0) BLB_TRACE(gp + 1, 13);
       const uint32_t o_addr = lane_addr + Cfg::O_COL;
-      __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + t * QT + row) * D + h * HD;
-      uint32_t r[32];
-      uint32_t rx[16];
-      tmem_ld_32x32(o_addr + wg * 32, r);               // this group's 32 of the 64 main O columns
-      if (Cfg::SPLIT_D && wg == 1) tmem_ld_32x16(o_addr + 64, rx);
+      tmem_ld_32x32(o_addr + wg * 32, o_r);               // this group's 32 of the 64 main O columns
+      if (Cfg::SPLIT_D && wg == 1) tmem_ld_32x16(o_addr + 64, reinterpret_cast<uint32_t(&)[16]>(o_rx[0]));
+      tmem_ld_32x1(lane_addr + Cfg::SUM_COL, o_sum);      // Σ_k P[row, k] from the ones-MMA
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);              // O is in registers: PV(g) may overwrite the accumulator
-      // stage the lane's 64-byte row slice in smem (16-byte piece j at j ^ ((row>>1)&3): conflict-free both ways),
-      // then store transposed so that one instruction writes 8 rows x 64 contiguous bytes instead of 32 x 16
-      const uint32_t ob = smem_u32(smem + Cfg::OFF_OST) + warp * 2048;
+      BLB_TRACE(gp + 1, 13);
+    };
+    auto epi_stage = [&](int gp) {
+      const float inv = 1.0f / __uint_as_float(o_sum);
+      // the lane's 64-byte row slice → smem (16-byte piece j at j ^ ((row>>1)&3): conflict-free both ways)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        pk.x = pack_bf16x2(__uint_as_float(o_r[8 * j]) * inv, __uint_as_float(o_r[8 * j + 1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(o_r[8 * j + 2]) * inv, __uint_as_float(o_r[8 * j + 3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(o_r[8 * j + 4]) * inv, __uint_as_float(o_r[8 * j + 5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(o_r[8 * j + 6]) * inv, __uint_as_float(o_r[8 * j + 7]) * inv);
         sts128(ob + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk);
       }
-      __syncwarp();
-      {
-        __nv_bfloat16* slab = out + (static_cast<size_t>(b) * T + t * QT + q * 32) * D + h * HD + wg * 32;
-        uint4 tv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int rr = k * 8 + (lane >> 2), j = lane & 3;
-          tv[k] = lds128(ob + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int rr = k * 8 + (lane >> 2), j = lane & 3;
-          stg128(slab + static_cast<size_t>(rr) * D + j * 8, tv[k]);
-        }
-      }
-      __syncwarp();
       if (Cfg::SPLIT_D && wg == 1) {
+        const int t = gp & 1, i = gp >> 1;
+        const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+        const int u = reverse ? n_units - 1 - u_i : u_i;
+        const int b = u / H, h = u - b * H;
         uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(rx[0]) * inv, __uint_as_float(rx[1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(rx[2]) * inv, __uint_as_float(rx[3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(rx[4]) * inv, __uint_as_float(rx[5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(rx[6]) * inv, __uint_as_float(rx[7]) * inv);
+        pk.x = pack_bf16x2(__uint_as_float(o_rx[0]) * inv, __uint_as_float(o_rx[1]) * inv);
+        pk.y = pack_bf16x2(__uint_as_float(o_rx[2]) * inv, __uint_as_float(o_rx[3]) * inv);
+        pk.z = pack_bf16x2(__uint_as_float(o_rx[4]) * inv, __uint_as_float(o_rx[5]) * inv);
+        pk.w = pack_bf16x2(__uint_as_float(o_rx[6]) * inv, __uint_as_float(o_rx[7]) * inv);
+        __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + t * QT + row) * D + h * HD;
         *reinterpret_cast<uint4*>(dst + 64) = pk;        // d 64..71 (72..79 are padding)
       }
-      if (warp == 0 && lane == 0) BLB_TRACE(gp + 1, 14);
+      __syncwarp();
+    };
+    auto epi_store = [&](int gp) {
+      const int t = gp & 1, i = gp >> 1;
+      const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      const int u = reverse ? n_units - 1 - u_i : u_i;
+      const int b = u / H, h = u - b * H;
+      __nv_bfloat16* slab = out + (static_cast<size_t>(b) * T + t * QT + q * 32) * D + h * HD + wg * 32;
+      uint4 tv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = k * 8 + (lane >> 2), j = lane & 3;
+        tv[k] = lds128(ob + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = k * 8 + (lane >> 2), j = lane & 3;
+        stg128(slab + static_cast<size_t>(rr) * D + j * 8, tv[k]);
+      }
+      __syncwarp();
+      BLB_TRACE(gp + 1, 14);
     };
 
     for (int g = 0; g < G; ++g) {
       mbar_wait(s_full, static_cast<uint32_t>(g & 1));
       tc_fence_after();
-      if (warp == 0 && lane == 0) BLB_TRACE(g, 8);
+      BLB_TRACE(g, 8);
       // ---- this thread's slice of the S row → registers in one pass, then release S ----
       uint32_t sv[Cfg::NREG_S];
 #pragma unroll
@@ -410,18 +510,20 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         tmem_ld_32x32(lane_addr + col_base + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[c * 32]));
       if (KX > 0) tmem_ld_32x8(lane_addr + tail_key0, reinterpret_cast<uint32_t(&)[8]>(sv[128]));
       tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < Cfg::NREG_S / 8; ++c) reg_fence8(&sv[c * 8]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
-      if (warp == 0 && lane == 0) BLB_TRACE(g, 9);
-      // ---- row max ----
+      BLB_TRACE(g, 9);
+      // ---- row max (3-input max, four independent chains) ----
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 128; j += 4) {
-        m0 = fmaxf(m0, __uint_as_float(sv[j]));
-        m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
-        m2 = fmaxf(m2, __uint_as_float(sv[j + 2]));
-        m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
+      for (int j = 0; j < 128; j += 8) {
+        m0 = fmax3(m0, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+        m1 = fmax3(m1, __uint_as_float(sv[j + 2]), __uint_as_float(sv[j + 3]));
+        m2 = fmax3(m2, __uint_as_float(sv[j + 4]), __uint_as_float(sv[j + 5]));
+        m3 = fmax3(m3, __uint_as_float(sv[j + 6]), __uint_as_float(sv[j + 7]));
       }
       if (KX > 0) {
 #pragma unroll
@@ -429,64 +531,93 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
           if (tail_key0 + j < T) m0 = fmaxf(m0, __uint_as_float(sv[128 + j]));
       }
       float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      xmax[wg * QT + row] = m;
-      asm volatile("bar.sync 1, 256;" ::: "memory");    // the two groups exchange their partial maxima
-      m = fmaxf(m, xmax[(wg ^ 1) * QT + row]);
+      xmax[(g & 1) * 2 * QT + wg * QT + row] = m;
+      pair_barrier(q);              // the two warps of this row quarter exchange their partial maxima
+      m = fmaxf(m, xmax[(g & 1) * 2 * QT + (wg ^ 1) * QT + row]);
       const float ms = m * scale_log2;
-      if (warp == 0 && lane == 0) BLB_TRACE(g, 10);
-      // The two groups are deliberately out of phase: group 1 drains the previous tile's O (epilogue: TMEM load,
-      // scale, coalesced stores — no MUFU) while group 0 already runs its exp2 stream, and group 0 does its half of
-      // that epilogue after its exp2s while group 1 is still in MUFU.  The MUFU pipe (the bottleneck of this kernel,
-      // 16 exp2/clk/SM) therefore sees a continuous stream instead of two warps per sub-partition stalling together.
-      if (wg == 1 && g > 0) epilogue(g - 1, sum_prev);
-      // P(g-1) must have been consumed by PV(g-1) before it is overwritten
-      if (g > 0) mbar_wait(p_empty, static_cast<uint32_t>((g - 1) & 1));
-      if (warp == 0 && lane == 0) BLB_TRACE(g, 11);
-      // ---- p = 2^(s*c - m*c), partial row sum, bf16 P → TMEM (16 packed columns per 32 keys) ----
-      float s0 = 0.f, s1 = 0.f;
+      BLB_TRACE(g, 10);
+      // ---- p = 2^(s*c - m*c) → bf16 P → TMEM in PCH chunks (CK keys = CK/2 packed columns each); the row sum is an
+      // MMA.  Chunk c is published (p_full[c]) one chunk late, after its tcgen05.st had a whole chunk of exp2s to
+      // complete; the epilogue of tile g-1 is threaded through the chunks (group 0 one chunk ahead of group 1 where
+      // there is room) so that the two warps of a sub-partition are not in their non-MUFU pieces at the same time.
+      constexpr int CK = 128 / PCH;
+#if BLB_ATTN_EPI_MODE == 1
+      // the two warps of a sub-partition take turns on the MUFU pipe: group 1 runs the (MUFU-free) epilogue of tile g-1
+      // while group 0 streams its exp2s alone, group 0 does its epilogue while group 1 finishes its exp2s
+      if (g > 0) {
+        epi_load(g - 1);
+        if (wg == 1) {
+          epi_stage(g - 1);
+          epi_store(g - 1);
+        }
+      }
+#endif
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+      for (int c = 0; c < PCH; ++c) {
+        if (g > 0) mbar_wait(&p_empty[c], static_cast<uint32_t>((g - 1) & 1));   // PV(g-1) consumed these P columns
+        uint32_t pk[CK / 2];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j]), scale_log2, -ms));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j + 1]), scale_log2, -ms));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j + 2]), scale_log2, -ms));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(sv[c * 32 + j + 3]), scale_log2, -ms));
-          s0 += p0 + p1;
-          s1 += p2 + p3;
+        for (int j = 0; j < CK; j += 4) {
+          const float t0 = fmaf(__uint_as_float(sv[c * CK + j]), scale_log2, -ms);
+          const float t1 = fmaf(__uint_as_float(sv[c * CK + j + 1]), scale_log2, -ms);
+          const float t2 = fmaf(__uint_as_float(sv[c * CK + j + 2]), scale_log2, -ms);
+          const float t3 = fmaf(__uint_as_float(sv[c * CK + j + 3]), scale_log2, -ms);
+          const float p0 = (BLB_ATTN_POLY_MASK & 1) ? exp2_poly(t0) : ex2_approx(t0);
+          const float p1 = (BLB_ATTN_POLY_MASK & 2) ? exp2_poly(t1) : ex2_approx(t1);
+          const float p2 = (BLB_ATTN_POLY_MASK & 4) ? exp2_poly(t2) : ex2_approx(t2);
+          const float p3 = (BLB_ATTN_POLY_MASK & 8) ? exp2_poly(t3) : ex2_approx(t3);
           pk[j / 2] = pack_bf16x2(p0, p1);
           pk[j / 2 + 1] = pack_bf16x2(p2, p3);
         }
-        tmem_st_32x16(lane_addr + Cfg::P_COL + (col_base + c * 32) / 2, pk);
-      }
-      if (KX > 0) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const float p0 = (tail_key0 + j < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j]), scale_log2, -ms)) : 0.f;
-          const float p1 =
-              (tail_key0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j + 1]), scale_log2, -ms)) : 0.f;
-          s0 += p0 + p1;
-          pk[j / 2] = pack_bf16x2(p0, p1);
+        if (c > 0) {                  // publish the previous chunk: its store was issued a whole chunk ago
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[c - 1]);
         }
-        tmem_st_32x4(lane_addr + Cfg::P_COL + tail_key0 / 2, pk);
+        if constexpr (CK == 32) tmem_st_32x16(lane_addr + Cfg::P_COL + (col_base + c * CK) / 2, pk);
+        else tmem_st_32x32(lane_addr + Cfg::P_COL + (col_base + c * CK) / 2, pk);
+        BLB_TRACE(g, 4 + c);
+        if (KX > 0 && c == PCH - 1) {
+          uint32_t pt[4];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float p0 = (tail_key0 + j < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j]), scale_log2, -ms)) : 0.f;
+            const float p1 =
+                (tail_key0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j + 1]), scale_log2, -ms)) : 0.f;
+            pt[j / 2] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x4(lane_addr + Cfg::P_COL + tail_key0 / 2, pt);
+        }
+#if BLB_ATTN_EPI_MODE == 0
+        if (g > 0) {
+          if (c == 0) epi_load(g - 1);
+          if (PCH >= 4) {
+            if (c == wg) epi_stage(g - 1);
+            if (c == wg + 1) epi_store(g - 1);
+          } else {
+            if (c == 0 && wg == 0) epi_stage(g - 1);
+            if (c == PCH - 1 && wg == 1) epi_stage(g - 1);
+            if (c == PCH - 1) epi_store(g - 1);
+          }
+        }
+#else
+        if (g > 0 && wg == 0 && c == PCH - 1) {   // group 0: whole epilogue after its exp2 stream
+          epi_stage(g - 1);
+          epi_store(g - 1);
+        }
+#endif
       }
-      const float sum = s0 + s1;
-      xsum[(g & 1) * 2 * QT + wg * QT + row] = sum;   // read by the other group in this tile's epilogue
-      tmem_st_wait();               // P is in TMEM
+      tmem_st_wait();               // the last chunk of P is in TMEM
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (warp == 0 && lane == 0) BLB_TRACE(g, 12);
-      // ---- epilogue of the previous tile (its PV ran underneath this tile's softmax; the other group's partial
-      //      sum of tile g-1 was published before this tile's bar.sync) ----
-      if (wg == 0 && g > 0) epilogue(g - 1, sum_prev);
-      sum_prev = sum;
+      if (lane == 0) mbar_arrive(&p_full[PCH - 1]);
+      BLB_TRACE(g, 12);
     }
     if (G > 0) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");    // partial sums of the last tile are visible
-      epilogue(G - 1, sum_prev);
+      epi_load(G - 1);
+      epi_stage(G - 1);
+      epi_store(G - 1);
     }
   }
 
@@ -534,8 +665,8 @@ int make_qkv_map(CUtensorMap* map, const void* qkv, int B, int T, int H, int hd,
 
 long long* g_attn_trace = nullptr;
 
-template <int HD, int KX>
-int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream, int reverse) {
+template <int HD, int KX, bool TRACE>
+int launch_tc_impl(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream, int reverse) {
   using Cfg = AttnCfg<HD, KX>;
   AttnMaps maps;
   int rc = make_qkv_map(&maps.q_main, qkv, B, T, H, HD, 64, QT, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -544,7 +675,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
   if (rc == 0) rc = make_qkv_map(&maps.q_x, qkv, B, T, H, HD, 16, QT, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc == 0) rc = make_qkv_map(&maps.kv_x, qkv, B, T, H, HD, 16, KMAIN, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != 0) return rc;
-  auto kern = attention_tc_kernel<HD, KX>;
+  auto kern = attention_tc_kernel<HD, KX, TRACE>;
   static bool configured[BLB_MAX_DEVICES] = {};   // the attribute is per device
   if (!configured[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -559,6 +690,13 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
   if (le != cudaSuccess) return static_cast<int>(le);
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
+}
+
+template <int HD, int KX>
+int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, cudaStream_t stream, int reverse) {
+  // the pipeline-trace instrumentation is a separate instantiation: the production kernel carries none of it
+  if (g_attn_trace != nullptr) return launch_tc_impl<HD, KX, true>(qkv, out, B, T, H, stream, reverse);
+  return launch_tc_impl<HD, KX, false>(qkv, out, B, T, H, stream, reverse);
 }
 
 }  // namespace

@@ -6,6 +6,7 @@ libbridgelang_b200.so and raises if the tensors are not CUDA tensors — there i
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Optional
 
@@ -34,7 +35,29 @@ def shared_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 
 def _stream() -> int:
+    """Raw handle of the current stream of the CURRENT device; only valid inside `on_device(...)`."""
     return torch.cuda.current_stream().cuda_stream
+
+
+@contextlib.contextmanager
+def on_device(*ts: Optional[torch.Tensor]):
+    """Device guard for a native call: every operand must live on ONE CUDA device, which becomes the current device
+    for the duration of the call — kernels, TMA descriptors, per-device one-time setup and the stream handed to the
+    library (`_stream()`) then all belong to the tensors' GPU, whatever device the caller had selected."""
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("bridgelang_b200 operators run on CUDA tensors only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"operands on different devices: {dev} vs {t.device}")
+    if dev is None:
+        raise RuntimeError("native call without a CUDA operand")
+    with torch.cuda.device(dev):
+        yield dev
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -80,8 +103,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, 
         assert xb_out.dtype == torch.bfloat16 and xb_out.stride(1) == 1 and tuple(xb_out.shape) == (M, N)
         e.xb_out, e.ld_xb = xb_out.data_ptr(), xb_out.stride(0)
     lib = _lib.load()
-    _lib.check(lib.blb_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, mode, C.byref(e),
-                                 _stream()), "gemm")
+    with on_device(a, w, bias, gamma, resid, out, pos, ln_stats, ln_colsum, stats_out, xb_out):
+        _lib.check(lib.blb_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, mode, C.byref(e),
+                                     _stream()), "gemm")
     return out
 
 
@@ -96,8 +120,10 @@ def rowstats_cast(x: torch.Tensor, parts: int):
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     stats = torch.empty((parts, x.shape[0], 2), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().blb_rowstats_cast(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), stats.data_ptr(),
-                                             parts, x.shape[0], x.shape[1], _stream()), "rowstats_cast")
+    with on_device(x):
+        _lib.check(_lib.load().blb_rowstats_cast(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0),
+                                                 stats.data_ptr(), parts, x.shape[0], x.shape[1], _stream()),
+                   "rowstats_cast")
     return y, stats
 
 
@@ -105,8 +131,10 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
     _need_cuda(x, weight, bias)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.load().blb_layernorm(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(), y.data_ptr(),
-                                         y.stride(0), x.shape[0], x.shape[1], eps, _stream()), "layernorm")
+    with on_device(x, weight, bias):
+        _lib.check(_lib.load().blb_layernorm(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(),
+                                             y.data_ptr(), y.stride(0), x.shape[0], x.shape[1], eps, _stream()),
+                   "layernorm")
     return y
 
 
@@ -115,8 +143,9 @@ def attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, head_dim: 
     _need_cuda(qkv)
     assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.shape == (batch * tokens, 3 * heads * head_dim)
     out = torch.empty((batch * tokens, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.load().blb_attention(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, head_dim, _stream()),
-               "attention")
+    with on_device(qkv):
+        _lib.check(_lib.load().blb_attention(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, head_dim,
+                                             _stream()), "attention")
     return out
 
 
@@ -125,7 +154,8 @@ def im2col_patch14(pixels: torch.Tensor, ldk: int = 592) -> torch.Tensor:
     assert pixels.dtype == torch.bfloat16 and pixels.is_contiguous() and pixels.shape[1:] == (3, 224, 224)
     B = pixels.shape[0]
     cols = torch.empty((B * 256, ldk), dtype=torch.bfloat16, device=pixels.device)
-    _lib.check(_lib.load().blb_im2col_patch14(pixels.data_ptr(), cols.data_ptr(), B, ldk, _stream()), "im2col")
+    with on_device(pixels):
+        _lib.check(_lib.load().blb_im2col_patch14(pixels.data_ptr(), cols.data_ptr(), B, ldk, _stream()), "im2col")
     return cols
 
 
@@ -137,8 +167,9 @@ def argmax(logits: torch.Tensor) -> torch.Tensor:
     _need_cuda(logits)
     assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in _DTYPES
     ids = torch.empty((logits.shape[0],), dtype=torch.int64, device=logits.device)
-    _lib.check(_lib.load().blb_argmax(logits.data_ptr(), _DTYPES[logits.dtype], logits.shape[0], logits.shape[1],
-                                      logits.stride(0), ids.data_ptr(), _stream()), "argmax")
+    with on_device(logits):
+        _lib.check(_lib.load().blb_argmax(logits.data_ptr(), _DTYPES[logits.dtype], logits.shape[0], logits.shape[1],
+                                          logits.stride(0), ids.data_ptr(), _stream()), "argmax")
     return ids
 
 
@@ -160,10 +191,11 @@ def detokenize_unnormalize(ids: torch.Tensor, vocab_size: int, tables: DecodeTab
     n = ids.numel()
     norm = torch.empty((n,), dtype=torch.float64, device=ids.device)
     act = torch.empty((n,), dtype=torch.float64, device=ids.device)
-    _lib.check(_lib.load().blb_detokenize_unnormalize(
-        ids.data_ptr(), n, vocab_size, tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim,
-        _ptr(tables.q01), _ptr(tables.q99), _ptr(tables.mask), norm.data_ptr(), act.data_ptr(), _stream()),
-        "detokenize_unnormalize")
+    with on_device(ids, tables.bin_centers, tables.q01, tables.q99, tables.mask):
+        _lib.check(_lib.load().blb_detokenize_unnormalize(
+            ids.data_ptr(), n, vocab_size, tables.bin_centers.data_ptr(), tables.bin_centers.numel(),
+            tables.action_dim, _ptr(tables.q01), _ptr(tables.q99), _ptr(tables.mask), norm.data_ptr(), act.data_ptr(),
+            _stream()), "detokenize_unnormalize")
     return norm, act
 
 
@@ -175,11 +207,12 @@ def argmax_detokenize_unnormalize(logits: torch.Tensor, vocab_size: int, tables:
     ids = torch.empty((rows,), dtype=torch.int64, device=logits.device)
     norm = torch.empty((rows,), dtype=torch.float64, device=logits.device)
     act = torch.empty((rows,), dtype=torch.float64, device=logits.device)
-    _lib.check(_lib.load().blb_argmax_detokenize_unnormalize(
-        logits.data_ptr(), _DTYPES[logits.dtype], rows, logits.shape[1], logits.stride(0), vocab_size,
-        tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim, _ptr(tables.q01),
-        _ptr(tables.q99), _ptr(tables.mask), ids.data_ptr(), norm.data_ptr(), act.data_ptr(), _stream()),
-        "argmax_detokenize_unnormalize")
+    with on_device(logits, tables.bin_centers, tables.q01, tables.q99, tables.mask):
+        _lib.check(_lib.load().blb_argmax_detokenize_unnormalize(
+            logits.data_ptr(), _DTYPES[logits.dtype], rows, logits.shape[1], logits.stride(0), vocab_size,
+            tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim, _ptr(tables.q01),
+            _ptr(tables.q99), _ptr(tables.mask), ids.data_ptr(), norm.data_ptr(), act.data_ptr(), _stream()),
+            "argmax_detokenize_unnormalize")
     return ids, norm, act
 
 
@@ -191,8 +224,9 @@ def preprocess_u8(frames: torch.Tensor, lut: torch.Tensor):
     B = frames.shape[0]
     dino = torch.empty((B, 3, 224, 224), dtype=torch.bfloat16, device=frames.device)
     siglip = torch.empty_like(dino)
-    _lib.check(_lib.load().blb_preprocess_u8(frames.data_ptr(), B, lut.data_ptr(), dino.data_ptr(), siglip.data_ptr(),
-                                             _stream()), "preprocess_u8")
+    with on_device(frames, lut):
+        _lib.check(_lib.load().blb_preprocess_u8(frames.data_ptr(), B, lut.data_ptr(), dino.data_ptr(),
+                                                 siglip.data_ptr(), _stream()), "preprocess_u8")
     return dino, siglip
 
 
@@ -206,9 +240,10 @@ def encode_actions(actions: torch.Tensor, bins: torch.Tensor, min_action: float,
     if a.numel() == 0:
         return ids
     dt = _lib.DTYPE_F32 if a.dtype == torch.float32 else _lib.DTYPE_F64
-    _lib.check(_lib.load().blb_encode_actions(a.data_ptr(), dt, a.numel(), bins.data_ptr(), bins.numel(),
-                                              float(min_action), float(max_action), int(vocab_size), ids.data_ptr(),
-                                              _stream()), "encode_actions")
+    with on_device(a, bins):
+        _lib.check(_lib.load().blb_encode_actions(a.data_ptr(), dt, a.numel(), bins.data_ptr(), bins.numel(),
+                                                  float(min_action), float(max_action), int(vocab_size),
+                                                  ids.data_ptr(), _stream()), "encode_actions")
     return ids
 
 
@@ -226,11 +261,12 @@ def action_token_metrics(logits: torch.Tensor, labels: torch.Tensor, num_patches
     absdiff = torch.empty((B, n_pos), dtype=torch.float64, device=logits.device)
     counts = torch.empty((2,), dtype=torch.int64, device=logits.device)
     l1_sum = torch.empty((1,), dtype=torch.float64, device=logits.device)
-    _lib.check(_lib.load().blb_action_token_metrics(
-        logits.data_ptr(), _DTYPES[logits.dtype], B, S, V, logits.stride(1), logits.stride(0), num_patches,
-        labels.data_ptr(), labels.stride(0), int(action_token_begin_idx), int(vocab_size), tables.bin_centers.data_ptr(),
-        tables.bin_centers.numel(), preds.data_ptr(), absdiff.data_ptr(), counts.data_ptr(), l1_sum.data_ptr(),
-        _stream()), "action_token_metrics")
+    with on_device(logits, labels, tables.bin_centers):
+        _lib.check(_lib.load().blb_action_token_metrics(
+            logits.data_ptr(), _DTYPES[logits.dtype], B, S, V, logits.stride(1), logits.stride(0), num_patches,
+            labels.data_ptr(), labels.stride(0), int(action_token_begin_idx), int(vocab_size),
+            tables.bin_centers.data_ptr(), tables.bin_centers.numel(), preds.data_ptr(), absdiff.data_ptr(),
+            counts.data_ptr(), l1_sum.data_ptr(), _stream()), "action_token_metrics")
     return {"preds": preds, "absdiff": absdiff, "counts": counts, "l1_sum": l1_sum}
 
 

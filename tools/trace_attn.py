@@ -1,26 +1,29 @@
-"""trace_attn.py — print the pipeline timeline (SM cycles) of the tcgen05 attention kernel, CTA 0, tiles 8..15."""
+"""trace_attn.py — print the pipeline timeline (SM cycles) of the tcgen05 attention kernel, CTA 0, tiles 8..15, per warp."""
 import sys
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from bridgelang_b200 import _lib, ops
 
-NAMES = {0: "mma:s_free(g) seen", 1: "mma:S(g+1) issued", 2: "mma:p_full(g)+o_empty seen", 3: "mma:PV(g) issued",
-         8: "sm:s_full(g) seen", 9: "sm:S in regs / s_free", 10: "sm:max exchanged", 11: "sm:p_empty(g-1) seen",
-         12: "sm:P stored / p_full(g)", 13: "sm:o_full(g-1) seen", 14: "sm:epilogue(g-1) done"}
+MMA = {0: "s_free(g) seen", 1: "S(g+1) issued", 2: "o_empty(g-1) seen", 3: "PV(g) issued", 4: "p_full[0] seen",
+       5: "p_full[1] seen", 6: "p_full[2] seen", 7: "p_full[3] seen", 8: "k_full seen", 9: "q_full seen"}
+SM = {8: "s_full", 9: "S in regs", 10: "max xchg", 4: "P0 st", 5: "P1 st", 6: "P2 st", 7: "P3 st", 12: "P3 published",
+      13: "O(g-1) in regs", 14: "epi(g-1) stored"}
 for (B, T, H, hd) in ((256, 261, 16, 64), (256, 256, 16, 72)):
     qkv = torch.randn(B * T, 3 * H * hd, device="cuda").bfloat16()
-    buf = torch.zeros(256, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(8 * 12 * 16, dtype=torch.int64, device="cuda")
     ops.attention(qkv, B, T, H, hd)
     _lib.load().blb_debug_attention_trace(buf.data_ptr())
     ops.attention(qkv, B, T, H, hd)
     torch.cuda.synchronize()
     _lib.load().blb_debug_attention_trace(None)
-    t = buf.cpu().view(-1, 16)
+    t = buf.cpu().view(8, 12, 16)
     t0 = int(t[0][t[0] > 0].min())
     print(f"==== T={T} hd={hd}")
-    for gi in range(8):
-        ev = [(int(t[gi, e]) - t0, NAMES[e]) for e in NAMES if t[gi, e] > 0]
-        for c, n in sorted(ev):
-            print(f"  g={gi + 8}  {c:8d}  {n}")
-        print()
+    for gi in range(1, 5):
+        print(f"-- tile g={gi + 8}")
+        order = [8, 9, 10, 4, 13, 5, 6, 14, 7, 12]
+        print("   warp " + " ".join(f"{SM[e]:>14s}" for e in order))
+        for w in range(8):
+            print(f"   {w:4d} " + " ".join(f"{int(t[gi, w, e]) - t0:14d}" for e in order))
+        print("   mma  " + "  ".join(f"{MMA[e]}={int(t[gi, 9, e]) - t0}" for e in (0, 8, 9, 1, 2, 4, 5, 6, 7, 3)))

@@ -7,7 +7,7 @@ include/bridgelang_b200.h (libbridgelang_b200.so, built in-tree by `python -m br
 
 from .action_tokenizer import ActionTokenizer
 from .config import DINOV2_L14_REG4, FUSED_DIM, LLM_DIM, SIGLIP_SO400M_14, VitConfig, fused_flops_per_image
-from .pipeline import VisualPrefixEncoder, gather_prefixes, shard_bounds, shard_pixel_values
+from .pipeline import PrefixGatherer, VisualPrefixEncoder, gather_prefixes, shard_bounds, shard_pixel_values
 from .projector import FusedMLPProjector, PrismaticProjector
 from .vision import (DinoSigLIPImageTransform, DinoSigLIPViTBackbone, DinoV2ViTBackbone, PrismaticImageProcessor,
                      PrismaticVisionBackbone, SigLIPViTBackbone, VisionBackbone, VisionTransformer)
@@ -15,7 +15,7 @@ from .vla import OpenVLA, OpenVLAForActionPrediction, PurePromptBuilder, decode_
 
 __all__ = [
     "ActionTokenizer", "DINOV2_L14_REG4", "SIGLIP_SO400M_14", "VitConfig", "FUSED_DIM", "LLM_DIM",
-    "fused_flops_per_image", "VisualPrefixEncoder", "gather_prefixes", "shard_bounds", "shard_pixel_values",
+    "fused_flops_per_image", "VisualPrefixEncoder", "PrefixGatherer", "gather_prefixes", "shard_bounds", "shard_pixel_values",
     "FusedMLPProjector", "PrismaticProjector", "DinoSigLIPImageTransform", "DinoSigLIPViTBackbone",
     "DinoV2ViTBackbone", "SigLIPViTBackbone", "PrismaticImageProcessor", "PrismaticVisionBackbone", "VisionBackbone", "VisionTransformer",
     "OpenVLA", "OpenVLAForActionPrediction", "PurePromptBuilder", "decode_tail_from_logits",

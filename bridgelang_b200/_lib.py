@@ -43,6 +43,7 @@ class VitWeights(C.Structure):
         ("n_prefix", C.c_int32), ("n_blocks", C.c_int32), ("patch_ldk", C.c_int32), ("ln_eps", C.c_float),
         ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("pos_embed", C.c_void_p), ("prefix", C.c_void_p),
         ("blocks_host", C.POINTER(BlockWeights)), ("ln_folded", C.c_int32),
+        ("hidden", C.c_int32),
     ]
 
 
@@ -93,6 +94,12 @@ _SIGNATURES = {
                                            C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "blb_argmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "blb_argmax_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p]),
+    "blb_argmax_window_detokenize_unnormalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int,
+                                                           C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                           C.c_void_p]),
     "blb_detokenize_unnormalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "blb_argmax_detokenize_unnormalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int,

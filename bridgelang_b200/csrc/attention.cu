@@ -12,6 +12,8 @@
 // 64-key blocks, bf16 mma.sync m16n8k16 with fp32 accumulation.
 #include <cstdlib>
 
+#include <atomic>
+
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -209,7 +211,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B,
   const int smem = (2 * TKP + 64) * PITCH * 2;
   if (smem > 227 * 1024) return BLB_ERR_SHAPE;
   auto kern = attention_kernel<HD, HDP>;
-  static int configured_smem[BLB_MAX_DEVICES] = {};   // the attribute is per device
+  static std::atomic<int> configured_smem[BLB_MAX_DEVICES];   // the attribute is per device
   if (smem > configured_smem[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -405,7 +407,7 @@ static int launch_attention_tail(const __nv_bfloat16* qkv, __nv_bfloat16* out, i
                                  cudaStream_t stream, int reverse) {
   constexpr int KEYS_W = 16 * TAIL_MAXBLK;
   const int smem = (16 + TAIL_WARPS * 2 * KEYS_W) * TAIL_PITCH * 2 + TAIL_WARPS * 16 * (2 + 64) * 4;
-  static bool configured[BLB_MAX_DEVICES] = {};
+  static std::atomic<bool> configured[BLB_MAX_DEVICES];
   if (!configured[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(attention_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);

@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <atomic>
+
 #include "gemm.h"
 #include "ptx.cuh"
 
@@ -676,7 +678,7 @@ int launch_tc_impl(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, i
   if (rc == 0) rc = make_qkv_map(&maps.kv_x, qkv, B, T, H, HD, 16, KMAIN, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc != 0) return rc;
   auto kern = attention_tc_kernel<HD, KX, TRACE>;
-  static bool configured[BLB_MAX_DEVICES] = {};   // the attribute is per device
+  static std::atomic<bool> configured[BLB_MAX_DEVICES];   // the attribute is per device
   if (!configured[current_device()]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);

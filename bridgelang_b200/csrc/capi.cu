@@ -99,6 +99,7 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
                            __nv_bfloat16* attn, __nv_bfloat16* big, __nv_bfloat16* xb, float2* stats,
                            cudaStream_t st) {
   const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
+  const double Hreal = w->hidden > 0 ? w->hidden : w->hidden_pad;   // algorithmic (unpadded) MLP width
   const int parts = gemm_stats_parts(D);
   if (parts <= 0) return BLB_ERR_SHAPE;
   BLB_TRY(rowstats_cast_f32_bf16(resid, D, xb, D, stats, parts, M, D, st));
@@ -142,6 +143,7 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
       e.ln_colsum = b.fc1_colsum;
       e.ln_parts = parts;
       e.ln_eps = w->ln_eps;
+      e.alg_work = 2.0 * M * Hreal * D;
       e.reverse = next_dir();
       BLB_TRY(gemm_bf16(xb, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
     }
@@ -163,6 +165,7 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
         e.xb_out = xb;
         e.ld_xb = D;
       }
+      e.alg_work = 2.0 * M * D * Hreal;
       e.reverse = next_dir();
       BLB_TRY(gemm_bf16(big, Hm, bf(b.fc2_w), Hm, M, D, Hm, EPI_RESIDUAL, e, st));
     }
@@ -181,6 +184,7 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.xn);
   __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(base + ws.big);
   const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
+  const double Hreal = w->hidden > 0 ? w->hidden : w->hidden_pad;   // algorithmic (unpadded) MLP width
 
   // --- PatchEmbed (+bias +pos_embed) and the cls/reg prefix rows: timm patch_embed + _pos_embed ---------
   BLB_TRY(im2col_patch14(bf(pixels), big, batch, w->patch_ldk, st));
@@ -193,6 +197,7 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
     e.tok_in = PATCHES;
     e.tok_out = T;
     e.tok_shift = w->n_prefix;
+    e.alg_work = 2.0 * batch * PATCHES * D * 588.0;   // K = 3·14·14; patch_ldk only pads the row pitch
     BLB_TRY(gemm_bf16(big, w->patch_ldk, bf(w->patch_w), w->patch_ldk, batch * PATCHES, D, w->patch_ldk, EPI_PATCH, e,
                       st));
   }
@@ -236,6 +241,7 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
       e.bias = b.fc1_b;
       e.out = big;
       e.ld_out = Hm;
+      e.alg_work = 2.0 * M * Hreal * D;
       e.reverse = r_mm;
       BLB_TRY(gemm_bf16(xn, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
     }
@@ -255,6 +261,7 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
         e.tok_out = PATCHES;
         e.tok_shift = -w->n_prefix;
       }
+      e.alg_work = 2.0 * M * D * Hreal;
       e.reverse = r_ln;
       BLB_TRY(gemm_bf16(big, Hm, bf(b.fc2_w), Hm, M, D, Hm, EPI_RESIDUAL, e, st));
     }
@@ -304,7 +311,7 @@ int projector_forward(const blb_projector_weights* w, const void* x, int ldx, in
 #pragma GCC visibility push(default)
 extern "C" {
 
-int blb_abi_version(void) { return 2; }
+int blb_abi_version(void) { return 3; }
 
 const char* blb_status_string(int status) {
   switch (status) {
@@ -482,6 +489,22 @@ int blb_action_token_metrics(const void* logits, int dtype, int batch, int seq, 
 
 int blb_argmax(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, void* stream) {
   return argmax_rows(logits, dtype, rows, vocab, ld, ids, as_stream(stream));
+}
+
+int blb_argmax_window(const void* logits, int dtype, int rows, int vocab, int64_t ld, int win_begin, int win_end,
+                      int64_t* ids, void* stream) {
+  return argmax_rows_window(logits, dtype, rows, vocab, ld, win_begin, win_end, ids, as_stream(stream));
+}
+
+int blb_argmax_window_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld,
+                                             int win_begin, int win_end, int vocab_size, const double* bin_centers,
+                                             int n_centers, int action_dim, const double* q01, const double* q99,
+                                             const uint8_t* mask, int64_t* ids, double* normalized_out,
+                                             double* actions_out, void* stream) {
+  if (bin_centers == nullptr) return BLB_ERR_ARG;
+  return argmax_window_detokenize_unnormalize(logits, dtype, rows, vocab, ld, win_begin, win_end, vocab_size, bin_centers,
+                                              n_centers, action_dim, q01, q99, mask, ids, normalized_out, actions_out,
+                                              as_stream(stream));
 }
 
 int blb_detokenize_unnormalize(const int64_t* ids, int n, int vocab_size, const double* bin_centers, int n_centers,

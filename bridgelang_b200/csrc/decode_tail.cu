@@ -90,12 +90,13 @@ __device__ __forceinline__ void detok_one(long long id, int j, int vocab_size, c
 
 template <typename T>
 __global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ logits, int vocab, long long ld,
-                                                      int64_t* __restrict__ ids, int vocab_size,
+                                                      int win_begin, int64_t* __restrict__ ids, int vocab_size,
                                                       const double* bin_centers, int n_centers, int action_dim,
                                                       const double* q01, const double* q99, const uint8_t* mask,
                                                       double* norm_out, double* act_out) {
   const int r = blockIdx.x;
-  const int best = block_argmax<T>(logits + static_cast<size_t>(r) * ld, vocab);
+  // `vocab` columns starting at win_begin (full-row mode: win_begin = 0, vocab = row length)
+  const int best = block_argmax<T>(logits + static_cast<size_t>(r) * ld + win_begin, vocab) + win_begin;
   if (threadIdx.x == 0) {
     ids[r] = best;
     if (bin_centers != nullptr)
@@ -232,27 +233,30 @@ int action_token_metrics(const void* logits, int dtype, int batch, int seq, int 
   return static_cast<int>(cudaGetLastError());
 }
 
-int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int vocab_size,
-                                  const double* bin_centers, int n_centers, int action_dim, const double* q01,
-                                  const double* q99,
-                                  const uint8_t* mask, int64_t* ids, double* norm_out, double* act_out,
-                                  cudaStream_t stream) {
+// full-row mode: [win_begin, win_end) = [0, vocab).  A window of <= 1024 columns is reduced by ONE warp with shuffles
+// (256 action bins: 8 elements per lane), wider ranges by a 1024-thread block (per-warp shuffles + one smem stage).
+int argmax_window_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int win_begin,
+                                         int win_end, int vocab_size, const double* bin_centers, int n_centers,
+                                         int action_dim, const double* q01, const double* q99, const uint8_t* mask,
+                                         int64_t* ids, double* norm_out, double* act_out, cudaStream_t stream) {
   if (logits == nullptr || ids == nullptr || rows <= 0 || vocab <= 0 || ld < vocab) return BLB_ERR_ARG;
+  if (win_begin < 0 || win_end > vocab || win_begin >= win_end) return BLB_ERR_ARG;
   if (bin_centers != nullptr && n_centers <= 0) return BLB_ERR_ARG;
-  const int threads = 1024;
+  const int width = win_end - win_begin;
+  const int threads = width <= 1024 ? 32 : 1024;
   switch (dtype) {
     case 0:
-      argmax_kernel<float><<<rows, threads, 0, stream>>>(static_cast<const float*>(logits), vocab, ld, ids,
+      argmax_kernel<float><<<rows, threads, 0, stream>>>(static_cast<const float*>(logits), width, ld, win_begin, ids,
                                                          vocab_size, bin_centers, n_centers, action_dim, q01, q99,
                                                          mask, norm_out, act_out);
       break;
     case 1:
-      argmax_kernel<__nv_bfloat16><<<rows, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), vocab,
-                                                                 ld, ids, vocab_size, bin_centers, n_centers,
+      argmax_kernel<__nv_bfloat16><<<rows, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), width,
+                                                                 ld, win_begin, ids, vocab_size, bin_centers, n_centers,
                                                                  action_dim, q01, q99, mask, norm_out, act_out);
       break;
     case 2:
-      argmax_kernel<__half><<<rows, threads, 0, stream>>>(static_cast<const __half*>(logits), vocab, ld, ids,
+      argmax_kernel<__half><<<rows, threads, 0, stream>>>(static_cast<const __half*>(logits), width, ld, win_begin, ids,
                                                           vocab_size, bin_centers, n_centers, action_dim, q01, q99,
                                                           mask, norm_out, act_out);
       break;
@@ -261,6 +265,21 @@ int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int v
   }
   count_launch(1);
   return static_cast<int>(cudaGetLastError());
+}
+
+int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int vocab_size,
+                                  const double* bin_centers, int n_centers, int action_dim, const double* q01,
+                                  const double* q99,
+                                  const uint8_t* mask, int64_t* ids, double* norm_out, double* act_out,
+                                  cudaStream_t stream) {
+  return argmax_window_detokenize_unnormalize(logits, dtype, rows, vocab, ld, 0, vocab, vocab_size, bin_centers,
+                                              n_centers, action_dim, q01, q99, mask, ids, norm_out, act_out, stream);
+}
+
+int argmax_rows_window(const void* logits, int dtype, int rows, int vocab, int64_t ld, int win_begin, int win_end,
+                       int64_t* ids, cudaStream_t stream) {
+  return argmax_window_detokenize_unnormalize(logits, dtype, rows, vocab, ld, win_begin, win_end, 0, nullptr, 0, 0,
+                                              nullptr, nullptr, nullptr, ids, nullptr, nullptr, stream);
 }
 
 int argmax_rows(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, cudaStream_t stream) {

@@ -47,6 +47,9 @@ struct GemmEpilogue {
   float2* stats_out = nullptr;
   __nv_bfloat16* xb_out = nullptr;
   int ld_xb = 0;
+  // algorithmic FLOPs of this launch for the timing records when N or K carry zero padding (fc1 / fc2 of SigLIP:
+  // Hm 4304 → 4352, patch embed: K 588 → 592); 0 → 2·M·N·K
+  double alg_work = 0.0;
 };
 
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, int M, int N, int K, int mode,
@@ -119,6 +122,8 @@ int write_prefix_tokens(const float* prefix, float* resid, int B, int T, int n_p
 
 // decode_tail.cu
 int argmax_rows(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, cudaStream_t stream);
+int argmax_rows_window(const void* logits, int dtype, int rows, int vocab, int64_t ld, int win_begin, int win_end,
+                       int64_t* ids, cudaStream_t stream);
 int detokenize_unnormalize(const int64_t* ids, int n, int vocab_size, const double* bin_centers, int n_centers,
                            int action_dim, const double* q01, const double* q99, const uint8_t* mask, double* norm_out,
                            double* act_out, cudaStream_t stream);
@@ -127,6 +132,11 @@ int argmax_detokenize_unnormalize(const void* logits, int dtype, int rows, int v
                                   const double* q99,
                                   const uint8_t* mask, int64_t* ids, double* norm_out, double* act_out,
                                   cudaStream_t stream);
+
+int argmax_window_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld, int win_begin,
+                                         int win_end, int vocab_size, const double* bin_centers, int n_centers,
+                                         int action_dim, const double* q01, const double* q99, const uint8_t* mask,
+                                         int64_t* ids, double* norm_out, double* act_out, cudaStream_t stream);
 
 int encode_actions(const void* actions, int dtype, int n, const double* bins, int n_bins, double lo, double hi,
                    int vocab_size, int64_t* ids, cudaStream_t stream);

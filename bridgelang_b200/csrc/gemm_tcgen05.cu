@@ -17,7 +17,9 @@
 // eligible warp id, so a TMA / MMA issue never queues behind the (ALU-heavy) epilogue warps, and their loops are
 // warp-uniform with a single elected lane so that descriptors stay in uniform registers.
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "gemm.h"
@@ -554,12 +556,14 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t
                       box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static int g_num_sms = 0;
-static int g_force_ctas = 0;   // 0 = auto, 1 / 2 = forced (tests and A/B measurements)
+// Process-wide state.  The library may be driven from several host threads (one per stream / device): counters and
+// switches are atomics, the per-launch timing records (a diagnostics facility, see blb_timing_*) sit behind a mutex.
+static std::atomic<int> g_num_sms_dev[BLB_MAX_DEVICES];
+static std::atomic<int> g_force_ctas{0};   // 0 = auto, 1 / 2 = forced (tests and A/B measurements)
 static bool g_resid_direct = getenv("BLB_RESID_DIRECT") != nullptr;   // A/B switch: residual via plain loads
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
 
-void gemm_set_cta_group(int ctas) { g_force_ctas = ctas; }
+void gemm_set_cta_group(int ctas) { g_force_ctas.store(ctas, std::memory_order_relaxed); }
 static int pick_bn(int N) { return N % 256 == 0 ? 256 : N % 192 == 0 ? 192 : N % 128 == 0 ? 128 : 0; }
 int gemm_stats_parts(int N) {
   const int bn = pick_bn(N);
@@ -573,29 +577,36 @@ bool pdl_enabled() {
 // ---- optional per-launch timing ------------------------------------------------------------------
 namespace {
 struct TimingRec { int cat; long long tag; double work; cudaEvent_t e0, e1; };
-bool g_timing = false;
+std::atomic<bool> g_timing{false};
+std::mutex g_timing_mu;                 // guards g_recs / g_event_pool
 std::vector<TimingRec> g_recs;
 std::vector<cudaEvent_t> g_event_pool;
-cudaEvent_t g_pending_e0 = nullptr;
-cudaEvent_t get_event() {
+thread_local cudaEvent_t g_pending_e0 = nullptr;   // begin event of the launch this thread is bracketing
+cudaEvent_t get_event() {               // caller holds g_timing_mu
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 }  // namespace
-void timing_enable(int on) { g_timing = on != 0; }
-bool timing_enabled() { return g_timing; }
-void timing_begin(cudaStream_t s) { g_pending_e0 = get_event(); cudaEventRecord(g_pending_e0, s); }
+void timing_enable(int on) { g_timing.store(on != 0); }
+bool timing_enabled() { return g_timing.load(std::memory_order_relaxed); }
+void timing_begin(cudaStream_t s) {
+  { std::lock_guard<std::mutex> lk(g_timing_mu); g_pending_e0 = get_event(); }
+  cudaEventRecord(g_pending_e0, s);
+}
 void timing_end(int cat, double work, cudaStream_t s, long long tag) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   cudaEvent_t e1 = get_event();
   cudaEventRecord(e1, s);
   g_recs.push_back({cat, tag, work, g_pending_e0, e1});
   g_pending_e0 = nullptr;
 }
 void timing_reset() {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   for (auto& r : g_recs) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
   g_recs.clear();
 }
 int timing_collect(int cat, double* ms, double* work, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   double t = 0, w = 0; long long n = 0;
   for (auto& r : g_recs) {
     if (r.cat != cat) continue;
@@ -610,6 +621,7 @@ int timing_collect(int cat, double* ms, double* work, long long* launches) {
   return 0;
 }
 int timing_records(int max_records, int* cat, long long* tag, double* ms, double* work) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
   int n = 0;
   for (auto& r : g_recs) {
     if (n >= max_records) break;
@@ -621,8 +633,8 @@ int timing_records(int max_records, int* cat, long long* tag, double* ms, double
   }
   return n;
 }
-long long launch_count() { return g_launches; }
-void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int current_device() {
   int dev = 0;
@@ -630,13 +642,14 @@ int current_device() {
   return dev;
 }
 
-int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+int num_sms() {   // of the CURRENT device (cached per device)
+  const int dev = current_device();
+  int n = g_num_sms_dev[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms_dev[dev].store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
 
 template <int BN, int CTAS, int MODE, int RTMA>
@@ -644,11 +657,11 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
                   const GemmEpilogue& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CTAS, RTMA, (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU)>;
   auto kern = gemm_bf16_kernel<BN, CTAS, MODE, RTMA>;
-  static bool configured[BLB_MAX_DEVICES] = {};   // the attribute is per device
-  if (!configured[current_device()]) {
+  static std::atomic<bool> configured[BLB_MAX_DEVICES];   // the attribute is per device; setting it twice is harmless
+  if (!configured[current_device()].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    configured[current_device()] = true;
+    configured[current_device()].store(true, std::memory_order_release);
   }
   const int tile_m = BM * CTAS;
   const int tiles = ((M + tile_m - 1) / tile_m) * (N / BN);
@@ -672,7 +685,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   // tag: epilogue mode | LN-folded consumer | stats/xb producer | N | K  (blb_timing_records)
   const long long tag = (static_cast<long long>(MODE) << 44) | (static_cast<long long>(epi.ln_stats != nullptr) << 43) |
                         (static_cast<long long>(epi.xb_out != nullptr) << 42) | (static_cast<long long>(N) << 20) | K;
-  TimingScope ts(TIME_GEMM, 2.0 * M * N * K, stream, tag);
+  TimingScope ts(TIME_GEMM, epi.alg_work > 0.0 ? epi.alg_work : 2.0 * M * N * K, stream, tag);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, M, N, K, epi);
   count_launch(1);
   return static_cast<int>(e);
@@ -707,7 +720,8 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   if (bn == 0) return BLB_ERR_SHAPE;
   if (epi.ln_stats != nullptr && (epi.ln_colsum == nullptr || epi.ln_parts <= 0 || mode > EPI_BIAS_GELU)) return BLB_ERR_ARG;
   if ((epi.stats_out != nullptr || epi.xb_out != nullptr) && mode != EPI_RESIDUAL) return BLB_ERR_ARG;
-  const int ctas = g_force_ctas != 0 ? g_force_ctas : 2;
+  const int forced = g_force_ctas.load(std::memory_order_relaxed);
+  const int ctas = forced != 0 ? forced : 2;
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_2d(&ta, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);
   if (rc != 0) return rc;

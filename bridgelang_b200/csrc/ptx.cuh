@@ -79,9 +79,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Every wait of every kernel goes through here.  A wrong tx-count or a missed arrive would otherwise be a silent hang
+// (and a gpurun strike): builds with -DBLB_BOUNDED_WAIT=<polls> (tests/tools: BLB_NVCC_EXTRA) trap after that many
+// unsuccessful polls — each try_wait already blocks for a hardware time slice, so 1<<22 polls is seconds, far beyond
+// any legitimate wait in these kernels — and the launch then fails with cudaErrorLaunchFailure instead of hanging.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef BLB_BOUNDED_WAIT
+  for (uint32_t polls = 0; !mbar_try_wait(bar, parity); ++polls)
+    if (polls > static_cast<uint32_t>(BLB_BOUNDED_WAIT)) asm volatile("trap;");
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------

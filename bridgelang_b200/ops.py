@@ -173,6 +173,19 @@ def argmax(logits: torch.Tensor) -> torch.Tensor:
     return ids
 
 
+def argmax_window(logits: torch.Tensor, begin: int, end: int) -> torch.Tensor:
+    """torch.argmax(logits[:, begin:end], -1) + begin — the explicit windowed mode (e.g. the 256 action bins
+    [31744, 32000)).  NOT the reference's greedy step, which arg-maxes the full row (`argmax`)."""
+    _need_cuda(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in _DTYPES
+    ids = torch.empty((logits.shape[0],), dtype=torch.int64, device=logits.device)
+    with on_device(logits):
+        _lib.check(_lib.load().blb_argmax_window(logits.data_ptr(), _DTYPES[logits.dtype], logits.shape[0],
+                                                 logits.shape[1], logits.stride(0), int(begin), int(end),
+                                                 ids.data_ptr(), _stream()), "argmax_window")
+    return ids
+
+
 class DecodeTables:
     """Device copies of bin_centers and the q01/q99/mask statistics of one dataset."""
 
@@ -213,6 +226,24 @@ def argmax_detokenize_unnormalize(logits: torch.Tensor, vocab_size: int, tables:
             tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim, _ptr(tables.q01),
             _ptr(tables.q99), _ptr(tables.mask), ids.data_ptr(), norm.data_ptr(), act.data_ptr(), _stream()),
             "argmax_detokenize_unnormalize")
+    return ids, norm, act
+
+
+def argmax_window_detokenize_unnormalize(logits: torch.Tensor, begin: int, end: int, vocab_size: int,
+                                         tables: DecodeTables):
+    """Windowed argmax (one warp per row, shuffle reduction) → bin centre → un-normalize in one launch."""
+    _need_cuda(logits)
+    assert logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in _DTYPES
+    rows = logits.shape[0]
+    ids = torch.empty((rows,), dtype=torch.int64, device=logits.device)
+    norm = torch.empty((rows,), dtype=torch.float64, device=logits.device)
+    act = torch.empty((rows,), dtype=torch.float64, device=logits.device)
+    with on_device(logits, tables.bin_centers, tables.q01, tables.q99, tables.mask):
+        _lib.check(_lib.load().blb_argmax_window_detokenize_unnormalize(
+            logits.data_ptr(), _DTYPES[logits.dtype], rows, logits.shape[1], logits.stride(0), int(begin), int(end),
+            vocab_size, tables.bin_centers.data_ptr(), tables.bin_centers.numel(), tables.action_dim,
+            _ptr(tables.q01), _ptr(tables.q99), _ptr(tables.mask), ids.data_ptr(), norm.data_ptr(), act.data_ptr(),
+            _stream()), "argmax_window_detokenize_unnormalize")
     return ids, norm, act
 
 

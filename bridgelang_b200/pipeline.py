@@ -62,11 +62,12 @@ class VisualPrefixEncoder(nn.Module):
         if B == 0:
             return (out, feats) if return_features else out
         need = lib.blb_fused_workspace_bytes(C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), B)
-        ws = ops.shared_workspace(dev, need)
-        _lib.check(lib.blb_fused_featurize_project_forward(
-            C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), dino_px.data_ptr(), siglip_px.data_ptr(), B,
-            feats.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
-            "fused_featurize_project_forward")
+        with ops.on_device(dino_px, siglip_px, self._towers[0].pos_embed, self._towers[1].pos_embed, feats, out):
+            ws = ops.shared_workspace(dev, need)
+            _lib.check(lib.blb_fused_featurize_project_forward(
+                C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), dino_px.data_ptr(), siglip_px.data_ptr(),
+                B, feats.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream().cuda_stream), "fused_featurize_project_forward")
         return (out, feats) if return_features else out
 
     @torch.no_grad()
@@ -78,11 +79,15 @@ class VisualPrefixEncoder(nn.Module):
         return self.forward(self.vision_backbone.preprocess_uint8(frames), return_features=return_features)
 
 
-    def stream(self, host_batches, uint8: bool = False):
+    def stream(self, host_batches, uint8: bool = False, to_host: bool = False):
         """Serving loop with double-buffered input staging: yields the projected prefix of every batch in
         `host_batches` (an iterable of pinned host `pixel_values` dicts / HF-packed tensors, or uint8 frame tensors
         with `uint8=True`), copying batch i+1 host→device on a side stream while batch i is being encoded.  Same
-        results as calling `forward` per batch; the H2D copy just leaves the critical path."""
+        results as calling `forward` per batch; the H2D copy just leaves the critical path.
+
+        `to_host=True` also brings every result back: the prefix is copied device→host into one of two pinned buffers
+        on a third stream (under the next batch's encode) and the generator yields `(host_tensor, done_event)` —
+        synchronize the event before reading; the buffer is reused two batches later."""
         dev = next(self.parameters()).device
         compute = torch.cuda.current_stream(dev)
         copier = torch.cuda.Stream(dev)
@@ -90,6 +95,19 @@ class VisualPrefixEncoder(nn.Module):
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         drained = [torch.cuda.Event(), torch.cuda.Event()]
         used = [False, False]
+        drainer = torch.cuda.Stream(dev) if to_host else None
+        host_out = [None, None]
+        out_done = [torch.cuda.Event(), torch.cuda.Event()]
+        keep_alive = [None, None]                 # device results whose D2H copy may still be running
+
+        def alloc_like(v):
+            # Allocate the staging buffer ON the copier stream: the caching allocator then never hands out a block
+            # that kernels already queued on the compute stream (e.g. the consumer's work on an earlier result) may
+            # still be reading, and record_stream tells it that the compute stream reads the buffer as well.
+            with torch.cuda.stream(copier):
+                t = torch.empty_like(v, device=dev)
+            t.record_stream(compute)
+            return t
 
         def upload(i, batch):
             # staging buffers mirror the host tensors' strides (empty_like): a layout mismatch would turn the async
@@ -97,9 +115,9 @@ class VisualPrefixEncoder(nn.Module):
             if isinstance(batch, dict):
                 if slots[i] is None or any(slots[i][k].shape != v.shape or slots[i][k].stride() != v.stride()
                                            for k, v in batch.items()):
-                    slots[i] = {k: torch.empty_like(v, device=dev) for k, v in batch.items()}
+                    slots[i] = {k: alloc_like(v) for k, v in batch.items()}
             elif slots[i] is None or slots[i].shape != batch.shape or slots[i].stride() != batch.stride():
-                slots[i] = torch.empty_like(batch, device=dev)
+                slots[i] = alloc_like(batch)
             with torch.cuda.stream(copier):
                 if used[i]:
                     copier.wait_event(drained[i])  # the encoder finished reading this slot
@@ -109,6 +127,20 @@ class VisualPrefixEncoder(nn.Module):
                 else:
                     slots[i].copy_(batch, non_blocking=True)
                 ready[i].record(copier)
+
+        def download(i, out):
+            if host_out[i] is None or host_out[i].shape != out.shape:
+                host_out[i] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            done = torch.cuda.Event()
+            done.record(compute)                   # the projector's last kernel
+            with torch.cuda.stream(drainer):
+                drainer.wait_event(done)
+                host_out[i].copy_(out, non_blocking=True)
+                out_done[i] = torch.cuda.Event()
+                out_done[i].record(drainer)
+            out.record_stream(drainer)
+            keep_alive[i] = out
+            return host_out[i], out_done[i]
 
         it = iter(host_batches)
         try:
@@ -124,7 +156,12 @@ class VisualPrefixEncoder(nn.Module):
             out = self.forward_uint8(slots[i]) if uint8 else self.forward(slots[i])
             drained[i].record(compute)
             used[i] = True
-            yield out
+            if to_host:
+                if host_out[i] is not None:
+                    out_done[i].synchronize()      # the consumer had a full batch of time to read this buffer
+                yield download(i, out)
+            else:
+                yield out
             if nxt is None:
                 return
             i = 1 - i
@@ -148,21 +185,67 @@ def shard_pixel_values(pixel_values: Dict[str, torch.Tensor], rank: int, world_s
     return {k: v[lo:hi] for k, v in pixel_values.items()}
 
 
-def gather_prefixes(local: torch.Tensor, global_batch: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """All-gather the per-rank projected prefixes [B_local, 256, llm_dim] into [global_batch, 256, llm_dim] on
-    every rank (NCCL over NVLink on GPUs).  Uneven shards are padded to the largest shard for the collective."""
+def _gather_layout(global_batch: int, world: int):
+    sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
+    return sizes, max(hi - lo for lo, hi in sizes)
+
+
+def _gather_into(local: torch.Tensor, global_batch: int, group) -> torch.Tensor:
+    """Enqueue the all-gather on the current stream; uneven shards are staged into one max-shard-sized send buffer
+    (a single allocation + one copy, the pad rows are never read by the caller)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
-    max_n = max(hi - lo for lo, hi in sizes)
+    sizes, max_n = _gather_layout(global_batch, world)
     lo, hi = sizes[rank]
     assert local.shape[0] == hi - lo, "local shard does not match shard_bounds()"
-    if local.shape[0] < max_n:
-        pad = torch.zeros((max_n - local.shape[0], *local.shape[1:]), dtype=local.dtype, device=local.device)
-        local = torch.cat([local, pad], dim=0)
+    send = local.contiguous()
+    if send.shape[0] < max_n:
+        staged = torch.empty((max_n, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        staged[:send.shape[0]].copy_(send)
+        send = staged
     gathered = torch.empty((world * max_n, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, local.contiguous(), group=group)
+    dist.all_gather_into_tensor(gathered, send, group=group)
     if all(h - l == max_n for l, h in sizes):
         return gathered
     parts: List[torch.Tensor] = [gathered[r * max_n: r * max_n + (h - l)] for r, (l, h) in enumerate(sizes)]
     return torch.cat(parts, dim=0)
+
+
+def gather_prefixes(local: torch.Tensor, global_batch: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather the per-rank projected prefixes [B_local, 256, llm_dim] into [global_batch, 256, llm_dim] on
+    every rank (NCCL over NVLink on GPUs), in line on the current stream."""
+    return _gather_into(local, global_batch, group)
+
+
+class PrefixGatherer:
+    """The same all-gather, taken off the critical path: `launch(local)` enqueues it on a communication stream (which
+    waits for the producer of `local`), `wait(handle)` makes the current stream wait for it and returns the gathered
+    tensor.  A serving loop calls launch() for step i, encodes step i+1, then wait()s — the 2 MiB per image that cross
+    NVLink (3.5 GiB received per rank at 8 x 256 images, ≈ 5 ms of a ≈ 100 ms step) move under the
+    next step's GEMMs instead of after this step's.  CPU tensors (gloo, the host-logic tests) run in line."""
+
+    def __init__(self, global_batch: int, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.global_batch, self.group = global_batch, group
+        self._stream: Optional[torch.cuda.Stream] = None
+
+    def launch(self, local: torch.Tensor):
+        if not local.is_cuda:
+            return (_gather_into(local, self.global_batch, self.group), None)
+        if self._stream is None or self._stream.device != local.device:
+            self._stream = torch.cuda.Stream(local.device)
+        produced = torch.cuda.Event()
+        produced.record(torch.cuda.current_stream(local.device))
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(produced)
+            out = _gather_into(local, self.global_batch, self.group)
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        local.record_stream(self._stream)
+        return (out, done)
+
+    def wait(self, handle) -> torch.Tensor:
+        out, done = handle
+        if done is not None:
+            torch.cuda.current_stream(out.device).wait_event(done)
+            out.record_stream(torch.cuda.current_stream(out.device))
+        return out

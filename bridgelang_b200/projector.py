@@ -81,11 +81,12 @@ class _ProjectorBase(nn.Module):
         if rows == 0:
             return out
         need = lib.blb_projector_workspace_bytes(C.byref(s), rows)
-        ws = ops.shared_workspace(x.device, need)
-        _lib.check(lib.blb_projector_forward(C.byref(s), x2.data_ptr(), x2.stride(0), rows, out.data_ptr(), ld_out,
-                                             tok_in, tok_out, tok_shift, ws.data_ptr(), ws.numel(),
-                                             torch.cuda.current_stream().cuda_stream),
-                   "projector_forward")
+        with ops.on_device(x2, out, self._linears()[0].weight):
+            ws = ops.shared_workspace(x.device, need)
+            _lib.check(lib.blb_projector_forward(C.byref(s), x2.data_ptr(), x2.stride(0), rows, out.data_ptr(), ld_out,
+                                                 tok_in, tok_out, tok_shift, ws.data_ptr(), ws.numel(),
+                                                 torch.cuda.current_stream().cuda_stream),
+                       "projector_forward")
         return out
 
 

@@ -171,10 +171,11 @@ class VisionTransformer(nn.Module):
         if B == 0:                      # an empty shard (more ranks than images): nothing to launch
             return
         need = lib.blb_vit_workspace_bytes(C.byref(pk.struct), B)
-        ws = self.workspace(need)
-        _lib.check(lib.blb_vit_tower_forward(C.byref(pk.struct), px.data_ptr(), B, out.data_ptr(), out.stride(-2),
-                                             col_off, ws.data_ptr(), ws.numel(),
-                                             torch.cuda.current_stream().cuda_stream), "vit_tower_forward")
+        with ops.on_device(px, out, self.pos_embed):   # kernels, TMA maps and the stream belong to the tensors' GPU
+            ws = self.workspace(need)
+            _lib.check(lib.blb_vit_tower_forward(C.byref(pk.struct), px.data_ptr(), B, out.data_ptr(), out.stride(-2),
+                                                 col_off, ws.data_ptr(), ws.numel(),
+                                                 torch.cuda.current_stream().cuda_stream), "vit_tower_forward")
 
     def forward(self, pixels: torch.Tensor) -> torch.Tensor:
         B = pixels.shape[0]
@@ -278,6 +279,7 @@ class _PackedTower:
         s.prefix = self.prefix.data_ptr() if self.prefix is not None else None
         s.blocks_host = C.cast(self.blocks, C.POINTER(_lib.BlockWeights))
         s.ln_folded = 1 if self.ln_folded else 0
+        s.hidden = Hm
         self.struct = s
 
 

@@ -100,6 +100,8 @@ typedef struct blb_vit_weights {
   const blb_block_weights* blocks_host; /* HOST array of n_blocks entries (device pointers inside) */
   int32_t ln_folded;  /* 1: no LayerNorm kernel - norm1/norm2 are folded into the qkv / fc1 GEMMs and their statistics come
                        * from the producing GEMM's epilogue; 0: explicit LayerNorm kernel before qkv / fc1 */
+  /* ---- ABI v3 ---- */
+  int32_t hidden;     /* unpadded MLP hidden (4096 / 4304): algorithmic FLOP accounting of the timing records; 0 = hidden_pad */
 } blb_vit_weights;
 
 /* prismatic/util/nn_utils.py:37-53 FusedMLPProjector == extern/hf/modeling_prismatic.py:146-158 fc1/fc2/fc3 */
@@ -206,6 +208,19 @@ int blb_action_token_metrics(const void* logits, int dtype, int batch, int seq, 
 /* ---- decode tail ---------------------------------------------------------------------------------------- */
 /* torch.argmax over each full logits row (first max wins; NaN maximal) -> int64 ids. */
 int blb_argmax(const void* logits, int dtype, int rows, int vocab, int64_t ld, int64_t* ids, void* stream);
+/* Windowed mode: torch.argmax(logits[:, win_begin:win_end], -1) + win_begin, e.g. [31744, 32000) = the 256 action bins of
+ * the 32000-entry tokenizer vocabulary (NOT the last 256 logits rows: 32000..32063 are <PAD> + padding, llama2.py:74-76).
+ * This is NOT what the reference's greedy step computes (it arg-maxes the full row, openvla.py:81-86) and equals
+ * blb_argmax only when the full-row winner lies inside the window - an explicit, opt-in mode for constrained decoding. */
+int blb_argmax_window(const void* logits, int dtype, int rows, int vocab, int64_t ld, int win_begin, int win_end,
+                      int64_t* ids, void* stream);
+/* the windowed argmax feeding the bin-centre lookup and the q01/q99 un-normalize in the same launch (one warp per row,
+ * shuffle reduction over the <= 1024 window columns). */
+int blb_argmax_window_detokenize_unnormalize(const void* logits, int dtype, int rows, int vocab, int64_t ld,
+                                             int win_begin, int win_end, int vocab_size, const double* bin_centers,
+                                             int n_centers, int action_dim, const double* q01, const double* q99,
+                                             const uint8_t* mask, int64_t* ids, double* normalized_out,
+                                             double* actions_out, void* stream);
 /* ActionTokenizer.decode_token_ids_to_actions (action_tokenizer.py:65-68) + un-normalize (openvla.py:94-101).
  * stats index = j %% action_dim; q01/q99/mask may be NULL (then actions == normalized). float64 bit-exact. */
 int blb_detokenize_unnormalize(const int64_t* ids, int n, int vocab_size, const double* bin_centers, int n_centers,

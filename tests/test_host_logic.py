@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.blb_abi_version() == 2
+    assert lib.blb_abi_version() == 3
     assert lib.blb_status_string(0) == b"ok"
     assert b"workspace" in lib.blb_status_string(-5)
 
@@ -182,7 +182,7 @@ def test_shard_bounds_cover_the_batch():
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["BLB_ROOT"])
-from bridgelang_b200.pipeline import gather_prefixes, shard_bounds, shard_pixel_values
+from bridgelang_b200.pipeline import PrefixGatherer, gather_prefixes, shard_bounds, shard_pixel_values
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["BLB_PORT"],
                         rank=int(os.environ["RANK"]), world_size=2)
 rank = dist.get_rank()
@@ -194,6 +194,8 @@ for global_batch in (6, 5):
     local = px["dino"] * 2            # stand-in for the per-rank featurize+project result
     out = gather_prefixes(local, global_batch)
     assert torch.equal(out, full * 2), (global_batch, rank)
+    g = PrefixGatherer(global_batch)              # launch / wait form (in line on CPU tensors)
+    assert torch.equal(g.wait(g.launch(local)), full * 2), (global_batch, rank)
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

@@ -28,6 +28,7 @@ class Epilogue(C.Structure):
         ("tok_in", C.c_int32), ("tok_out", C.c_int32), ("tok_shift", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p), ("xb_out", C.c_void_p), ("ld_xb", C.c_int32),
+        ("shift_in", C.c_void_p), ("shift_out", C.c_void_p),
     ]
 
 
@@ -71,7 +72,7 @@ _SIGNATURES = {
                                 C.POINTER(Epilogue), C.c_void_p]),
     "blb_gemm_stats_parts": (C.c_int, [C.c_int]),
     "blb_rowstats_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                    C.c_void_p]),
+                                    C.c_void_p, C.c_void_p]),
     "blb_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_float, C.c_void_p]),
     "blb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

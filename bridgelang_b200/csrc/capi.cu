@@ -21,7 +21,7 @@ constexpr int PATCHES = 256;  // 224 / 14 squared
 const bool g_serpentine = getenv("BLB_NO_SERPENTINE") == nullptr;   // A/B switch for the L2-aware row order
 
 struct TowerWs {
-  size_t resid, xn, big, xb, stats, total;
+  size_t resid, xn, big, xb, stats, shift, shift_bytes, total;
 };
 
 // resid fp32 [M,D] | xn bf16 [M,D] (LayerNorm out, then attention out) | big bf16 [M, max(3D, Hm_pad)]
@@ -37,7 +37,9 @@ TowerWs tower_ws(const blb_vit_weights* w, int batch) {
   s.big = s.xn + align_up(M * D * 2);
   s.xb = s.big + align_up(M * wide * 2);
   s.stats = s.xb + (w->ln_folded ? align_up(M * D * 2) : 0);
-  s.total = s.stats + (w->ln_folded ? align_up(M * static_cast<size_t>(gemm_stats_parts(w->dim)) * 8) : 0);
+  s.shift = s.stats + (w->ln_folded ? align_up(M * static_cast<size_t>(gemm_stats_parts(w->dim)) * 8) : 0);
+  s.shift_bytes = w->ln_folded ? align_up(M * 4) : 0;   // two buffers: a folded consumer reads one and writes the other
+  s.total = s.shift + 2 * s.shift_bytes;
   return s;
 }
 
@@ -97,12 +99,33 @@ TowerOverlap* tower_overlap_ctx() {
 // 5 launches per block instead of 7; the residual stream is read once and written once per branch.
 int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int ld_out, int out_col_off, float* resid,
                            __nv_bfloat16* attn, __nv_bfloat16* big, __nv_bfloat16* xb, float2* stats,
-                           cudaStream_t st) {
+                           float* shift2[2], cudaStream_t st) {
   const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
   const double Hreal = w->hidden > 0 ? w->hidden : w->hidden_pad;   // algorithmic (unpadded) MLP width
   const int parts = gemm_stats_parts(D);
   if (parts <= 0) return BLB_ERR_SHAPE;
-  BLB_TRY(rowstats_cast_f32_bf16(resid, D, xb, D, stats, parts, M, D, st));
+  // xb, the statistics and the consumers' algebra all live in "x minus a per-row shift" coordinates; the shift is the
+  // row mean one residual update ago: rowstats_cast primes it, every folded consumer (which rebuilds the mean anyway)
+  // rolls it forward for the producer that follows (BLB_LN_NO_SHIFT=1: c = 0, the round-1 fold)
+  static const bool use_shift = getenv("BLB_LN_NO_SHIFT") == nullptr;
+  int cur = 0;   // which shift buffer belongs to the current xb / stats
+  BLB_TRY(rowstats_cast_f32_bf16(resid, D, xb, D, stats, parts, M, D, st, use_shift ? shift2[cur] : nullptr));
+  auto consumer = [&](GemmEpilogue& e) {
+    e.ln_stats = stats;
+    e.ln_parts = parts;
+    e.ln_eps = w->ln_eps;
+    if (use_shift) {
+      e.shift_in = shift2[cur];
+      e.shift_out = shift2[cur ^ 1];
+      cur ^= 1;
+    }
+  };
+  auto producer = [&](GemmEpilogue& e) {
+    e.stats_out = stats;
+    e.xb_out = xb;
+    e.ld_xb = D;
+    if (use_shift) e.shift_in = shift2[cur];
+  };
   int rev = 0;   // serpentine: every kernel walks its rows opposite to its producer (see tower_forward)
   auto next_dir = [&]() { if (g_serpentine) rev ^= 1; return rev; };
   for (int i = 0; i < w->n_blocks; ++i) {
@@ -114,10 +137,8 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
       e.bias = b.qkv_b;
       e.out = big;
       e.ld_out = 3 * D;
-      e.ln_stats = stats;
       e.ln_colsum = b.qkv_colsum;
-      e.ln_parts = parts;
-      e.ln_eps = w->ln_eps;
+      consumer(e);
       e.reverse = next_dir();
       BLB_TRY(gemm_bf16(xb, D, bf(b.qkv_w), D, M, 3 * D, D, EPI_BIAS, e, st));
     }
@@ -128,9 +149,7 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
       e.gamma = b.ls1;
       e.resid = resid;
       e.ld_resid = D;
-      e.stats_out = stats;
-      e.xb_out = xb;
-      e.ld_xb = D;
+      producer(e);
       e.reverse = next_dir();
       BLB_TRY(gemm_bf16(attn, D, bf(b.proj_w), D, M, D, D, EPI_RESIDUAL, e, st));
     }
@@ -139,10 +158,8 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
       e.bias = b.fc1_b;
       e.out = big;
       e.ld_out = Hm;
-      e.ln_stats = stats;
       e.ln_colsum = b.fc1_colsum;
-      e.ln_parts = parts;
-      e.ln_eps = w->ln_eps;
+      consumer(e);
       e.alg_work = 2.0 * M * Hreal * D;
       e.reverse = next_dir();
       BLB_TRY(gemm_bf16(xb, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
@@ -161,9 +178,7 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
         e.tok_out = PATCHES;
         e.tok_shift = -w->n_prefix;
       } else {
-        e.stats_out = stats;
-        e.xb_out = xb;
-        e.ld_xb = D;
+        producer(e);
       }
       e.alg_work = 2.0 * M * D * Hreal;
       e.reverse = next_dir();
@@ -202,10 +217,13 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
                       st));
   }
   BLB_TRY(write_prefix_tokens(w->prefix, resid, batch, T, w->n_prefix, D, st));
-  if (w->ln_folded)
+  if (w->ln_folded) {
+    float* shift2[2] = {reinterpret_cast<float*>(base + ws.shift),
+                        reinterpret_cast<float*>(base + ws.shift + ws.shift_bytes)};
     return tower_blocks_ln_folded(w, batch, out, ld_out, out_col_off, resid, xn, big,
                                   reinterpret_cast<__nv_bfloat16*>(base + ws.xb),
-                                  reinterpret_cast<float2*>(base + ws.stats), st);
+                                  reinterpret_cast<float2*>(base + ws.stats), shift2, st);
+  }
 
   // --- timm Block x n_blocks:  x += ls1(attn(norm1(x)));  x += ls2(mlp(norm2(x))) -----------------------
   // Every kernel walks its rows in the direction opposite to its producer (serpentine), so it starts on the data the
@@ -363,6 +381,8 @@ int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
   e.stats_out = reinterpret_cast<float2*>(epi->stats_out);
   e.xb_out = bf(epi->xb_out);
   e.ld_xb = epi->ld_xb;
+  e.shift_in = epi->shift_in;
+  e.shift_out = epi->shift_out;
   if (e.xb_out != nullptr && e.ld_xb % 8 != 0) return BLB_ERR_ARG;
   if (mode == EPI_BIAS || mode == EPI_BIAS_GELU) {
     if (e.out == nullptr || e.ld_out % 8 != 0 || e.out_col_off % 8 != 0) return BLB_ERR_ARG;
@@ -380,9 +400,9 @@ int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
 int blb_gemm_stats_parts(int N) { return N > 0 ? gemm_stats_parts(N) : 0; }
 
 int blb_rowstats_cast(const float* x, int ldx, void* y, int ldy, float* stats, int parts, int rows, int D,
-                      void* stream) {
+                      float* shift, void* stream) {
   return rowstats_cast_f32_bf16(x, ldx, bf(y), ldy, reinterpret_cast<float2*>(stats), parts, rows, D,
-                                as_stream(stream));
+                                as_stream(stream), shift);
 }
 
 int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void* y, int ldy, int rows, int D,

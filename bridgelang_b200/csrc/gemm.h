@@ -47,6 +47,14 @@ struct GemmEpilogue {
   float2* stats_out = nullptr;
   __nv_bfloat16* xb_out = nullptr;
   int ld_xb = 0;
+  // rolling per-row shift (makes the fold independent of the row mean): xb, the statistics and the
+  // consumer's algebra live in "x − c_m" coordinates, c_m = the row mean one residual update ago.
+  //   producer (EPI_RESIDUAL): c_m = shift_in[m]; stores xb = bf16(x_new − c_m) and the statistics of x_new − c_m
+  //   consumer (folded BIAS / BIAS_GELU): unchanged algebra ((x − c) − mean(x − c) = x − mean(x)); it rebuilds
+  //     mean(x − c) anyway, so it also hands the next producer its shift: shift_out[m] = shift_in[m] + mean(x − c)
+  // nullptr: c = 0.  shift_in and shift_out must be different buffers (other CTAs still read shift_in).
+  const float* shift_in = nullptr;
+  float* shift_out = nullptr;
   // algorithmic FLOPs of this launch for the timing records when N or K carry zero padding (fc1 / fc2 of SigLIP:
   // Hm 4304 → 4352, patch embed: K 588 → 592); 0 → 2·M·N·K
   double alg_work = 0.0;
@@ -105,7 +113,7 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
 // fp32 rows → bf16 copy + full-row (sum, sumsq) in part 0 of `parts` (others zero): primes the LN-folded chain after
 // the patch-embed stage (the later blocks get both from the EPI_RESIDUAL epilogues)
 int rowstats_cast_f32_bf16(const float* x, int ldx, __nv_bfloat16* y, int ldy, float2* stats, int parts, int rows,
-                           int D, cudaStream_t stream);
+                           int D, cudaStream_t stream, float* shift = nullptr);
 
 // attention.cu — softmax(q kᵀ · hd^-0.5) v over packed qkv [B*T, 3*H*hd] → out [B*T, H*hd]
 int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,

@@ -290,9 +290,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const float inv_k = 1.0f / static_cast<float>(K);
           ln_mean = s1 * inv_k;
           ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mean * ln_mean, 0.f) + epi.ln_eps);
+          // rolling shift: the rows and their statistics are relative to shift_in; the absolute row mean = shift_in +
+          // ln_mean becomes the shift of the NEXT producer (one store per row: the first column span's warp)
+          if (epi.shift_out != nullptr && n_blk == 0 && half == 0)
+            epi.shift_out[row] = (epi.shift_in != nullptr ? __ldg(epi.shift_in + row) : 0.f) + ln_mean;
         }
       }
       float part_sum = 0.f, part_sq = 0.f;   // producer side: this lane's row over this warp's column span
+      // producer side, rolling shift: c = this row's mean one residual update ago, handed over by the folded consumer
+      // that ran in between (it rebuilds the mean anyway); the bf16 copy and the statistics below are those of x_new − c
+      float row_shift = 0.f;
+      if constexpr (MODE == EPI_RESIDUAL) {
+        if (epi.shift_in != nullptr && row_ok) row_shift = __ldg(epi.shift_in + row);
+      }
 
       // this warp's COLS_PER_WARP-wide slices of bias (vec 0) and of gamma | LN column sums (vec 1) → smem
       {
@@ -416,8 +426,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              part_sum += v[j];
-              part_sq = fmaf(v[j], v[j], part_sq);
+              const float a = v[j] - row_shift;
+              part_sum += a;
+              part_sq = fmaf(a, a, part_sq);
             }
             if constexpr (!RTMA) {
               if (epi.xb_out != nullptr) {
@@ -425,10 +436,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                   uint4 pk;
-                  pk.x = pack_bf16x2(v[j], v[j + 1]);
-                  pk.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                  pk.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                  pk.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  pk.x = pack_bf16x2(v[j] - row_shift, v[j + 1] - row_shift);
+                  pk.y = pack_bf16x2(v[j + 2] - row_shift, v[j + 3] - row_shift);
+                  pk.z = pack_bf16x2(v[j + 4] - row_shift, v[j + 5] - row_shift);
+                  pk.w = pack_bf16x2(v[j + 6] - row_shift, v[j + 7] - row_shift);
                   *reinterpret_cast<uint4*>(o + j) = pk;
                 }
               }
@@ -472,10 +483,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int r = k * 4 + (lane >> 3), j = lane & 7;
+                const float cr = __shfl_sync(0xffffffffu, row_shift, r);   // row r of the slab belongs to lane r
                 if (row0 + r < M) {
                   uint2 pk;
-                  pk.x = pack_bf16x2(__uint_as_float(tv[k].x), __uint_as_float(tv[k].y));
-                  pk.y = pack_bf16x2(__uint_as_float(tv[k].z), __uint_as_float(tv[k].w));
+                  pk.x = pack_bf16x2(__uint_as_float(tv[k].x) - cr, __uint_as_float(tv[k].y) - cr);
+                  pk.y = pack_bf16x2(__uint_as_float(tv[k].z) - cr, __uint_as_float(tv[k].w) - cr);
                   *reinterpret_cast<uint2*>(epi.xb_out + static_cast<size_t>(row0 + r) * epi.ld_xb + col0 + j * 4) = pk;
                 }
               }
@@ -720,6 +732,8 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   if (bn == 0) return BLB_ERR_SHAPE;
   if (epi.ln_stats != nullptr && (epi.ln_colsum == nullptr || epi.ln_parts <= 0 || mode > EPI_BIAS_GELU)) return BLB_ERR_ARG;
   if ((epi.stats_out != nullptr || epi.xb_out != nullptr) && mode != EPI_RESIDUAL) return BLB_ERR_ARG;
+  if (epi.shift_out != nullptr && (epi.ln_stats == nullptr || epi.shift_in == epi.shift_out)) return BLB_ERR_ARG;   // ping-pong
+  if (epi.shift_in != nullptr && mode == EPI_PATCH) return BLB_ERR_ARG;
   const int forced = g_force_ctas.load(std::memory_order_relaxed);
   const int ctas = forced != 0 ? forced : 2;
   CUtensorMap ta, tb;

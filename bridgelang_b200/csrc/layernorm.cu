@@ -75,12 +75,14 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
   return static_cast<int>(cudaGetLastError());
 }
 
-// Primer of the LN-folded chain: bf16 copy of the fp32 rows + their (sum, sum of squares).
-// Runs once per tower, after the patch-embed stage; every later block gets both from the EPI_RESIDUAL epilogues.
+// Primer of the LN-folded chain: per row the exact mean c (→ shift), the bf16 copy of x − c and the
+// (sum, sum of squares) of x − c.  Runs once per tower, after the patch-embed stage; every later block gets all three
+// from the EPI_RESIDUAL epilogues (which roll the shift forward, see gemm_tcgen05.cu).  shift == nullptr: c = 0.
 template <int VEC>
 __global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restrict__ x, int ldx,
                                                             __nv_bfloat16* __restrict__ y, int ldy,
-                                                            float2* __restrict__ stats, int parts, int rows) {
+                                                            float2* __restrict__ stats, int parts, int rows,
+                                                            float* __restrict__ shift) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = static_cast<int>(blockIdx.x) * 8 + warp;
   pdl_launch_dependents();
@@ -88,28 +90,39 @@ __global__ void __launch_bounds__(256) rowstats_cast_kernel(const float* __restr
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
-  float s = 0.f, q = 0.f;
+  float4 v[VEC];
+  float s = 0.f;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
-    const float4 v = xr[lane + 32 * j];
-    s += (v.x + v.y) + (v.z + v.w);
-    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    v[j] = xr[lane + 32 * j];
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float c = shift != nullptr ? s / static_cast<float>(VEC * 128) : 0.f;
+  float s1 = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float a0 = v[j].x - c, a1 = v[j].y - c, a2 = v[j].z - c, a3 = v[j].w - c;
+    s1 += (a0 + a1) + (a2 + a3);
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
     uint2 o;
-    o.x = pack_bf16x2(v.x, v.y);
-    o.y = pack_bf16x2(v.z, v.w);
+    o.x = pack_bf16x2(a0, a1);
+    o.y = pack_bf16x2(a2, a3);
     yr[lane + 32 * j] = o;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
   for (int p = lane; p < parts; p += 32)   // stats are [part][row]
-    stats[static_cast<size_t>(p) * rows + row] = p == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+    stats[static_cast<size_t>(p) * rows + row] = p == 0 ? make_float2(s1, q) : make_float2(0.f, 0.f);
+  if (shift != nullptr && lane == 0) shift[row] = c;
 }
 
 int rowstats_cast_f32_bf16(const float* x, int ldx, __nv_bfloat16* y, int ldy, float2* stats, int parts, int rows,
-                           int D, cudaStream_t stream) {
+                           int D, cudaStream_t stream, float* shift) {
   if (x == nullptr || y == nullptr || stats == nullptr || rows <= 0 || parts <= 0) return BLB_ERR_ARG;
   if (D % 128 != 0 || D > 2048 || ldx % 4 != 0 || ldy % 4 != 0) return BLB_ERR_SHAPE;
   const dim3 grid((rows + 7) / 8), block(256);
@@ -117,7 +130,7 @@ int rowstats_cast_f32_bf16(const float* x, int ldx, __nv_bfloat16* y, int ldy, f
   TimingScope ts(TIME_LAYERNORM, 6.0 * rows * D, stream);
   switch (D / 128) {
 #define BLB_RS_CASE(V) \
-  case V: le = launch_pdl(rowstats_cast_kernel<V>, grid, block, 0, stream, x, ldx, y, ldy, stats, parts, rows); break;
+  case V: le = launch_pdl(rowstats_cast_kernel<V>, grid, block, 0, stream, x, ldx, y, ldy, stats, parts, rows, shift); break;
     BLB_RS_CASE(1) BLB_RS_CASE(2) BLB_RS_CASE(3) BLB_RS_CASE(4) BLB_RS_CASE(5) BLB_RS_CASE(6) BLB_RS_CASE(7)
     BLB_RS_CASE(8) BLB_RS_CASE(9) BLB_RS_CASE(10) BLB_RS_CASE(11) BLB_RS_CASE(12) BLB_RS_CASE(13)
     BLB_RS_CASE(14) BLB_RS_CASE(15) BLB_RS_CASE(16)

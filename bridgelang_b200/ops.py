@@ -72,13 +72,16 @@ def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, resid=None, out=None,
          out_col_off: int = 0, pos=None, tok_in: int = 0, tok_out: int = 0, tok_shift: int = 0,
-         ln_stats=None, ln_colsum=None, ln_eps: float = 1e-6, stats_out=None, xb_out=None) -> Optional[torch.Tensor]:
+         ln_stats=None, ln_colsum=None, ln_eps: float = 1e-6, stats_out=None, xb_out=None, shift_in=None,
+         shift_out=None) -> Optional[torch.Tensor]:
     """C = a[M,K] @ w[N,K]^T with the fused epilogue `mode` (see include/bridgelang_b200.h).
 
     ln_stats [parts, M, 2] + ln_colsum [N]: LayerNorm folded into a BIAS / BIAS_GELU GEMM (a = bf16 copy of the
     un-normalised rows, w = W·diag(ln_w), bias = b + W·ln_b).  stats_out [gemm_stats_parts(N), M, 2] / xb_out [M, N]:
-    what a RESIDUAL GEMM emits for such a consumer."""
-    _need_cuda(a, w, bias, gamma, resid, out, pos, ln_stats, ln_colsum, stats_out, xb_out)
+    what a RESIDUAL GEMM emits for such a consumer.  Rolling per-row shift: a RESIDUAL GEMM with shift_in [M] emits
+    xb_out / stats_out of x_new − shift_in; a folded consumer with shift_in (+ shift_out [M]) writes the next
+    producer's shift, shift_out = shift_in + mean(x − shift_in)."""
+    _need_cuda(a, w, bias, gamma, resid, out, pos, ln_stats, ln_colsum, stats_out, xb_out, shift_in, shift_out)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
@@ -102,8 +105,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, 
     if xb_out is not None:
         assert xb_out.dtype == torch.bfloat16 and xb_out.stride(1) == 1 and tuple(xb_out.shape) == (M, N)
         e.xb_out, e.ld_xb = xb_out.data_ptr(), xb_out.stride(0)
+    if shift_in is not None:
+        assert shift_in.dtype == torch.float32 and shift_in.numel() == M and shift_in.is_contiguous()
+        e.shift_in = shift_in.data_ptr()
+    if shift_out is not None:
+        assert shift_out.dtype == torch.float32 and shift_out.numel() == M and shift_out.is_contiguous()
+        e.shift_out = shift_out.data_ptr()
     lib = _lib.load()
-    with on_device(a, w, bias, gamma, resid, out, pos, ln_stats, ln_colsum, stats_out, xb_out):
+    with on_device(a, w, bias, gamma, resid, out, pos, ln_stats, ln_colsum, stats_out, xb_out, shift_in, shift_out):
         _lib.check(lib.blb_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, mode, C.byref(e),
                                      _stream()), "gemm")
     return out
@@ -114,17 +123,19 @@ def gemm_stats_parts(n: int) -> int:
     return int(_lib.load().blb_gemm_stats_parts(int(n)))
 
 
-def rowstats_cast(x: torch.Tensor, parts: int):
-    """fp32 rows → (bf16 copy, stats [parts, rows, 2] with the full-row (sum, sumsq) in part 0)."""
+def rowstats_cast(x: torch.Tensor, parts: int, with_shift: bool = False):
+    """fp32 rows → (bf16 copy, stats [parts, rows, 2] with the full-row (sum, sumsq) in part 0).  with_shift: both are
+    those of x − c with c = the row mean, and the third return value is c [rows] (the primer of the rolling shift)."""
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     stats = torch.empty((parts, x.shape[0], 2), dtype=torch.float32, device=x.device)
+    shift = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device) if with_shift else None
     with on_device(x):
         _lib.check(_lib.load().blb_rowstats_cast(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0),
-                                                 stats.data_ptr(), parts, x.shape[0], x.shape[1], _stream()),
-                   "rowstats_cast")
-    return y, stats
+                                                 stats.data_ptr(), parts, x.shape[0], x.shape[1], _ptr(shift),
+                                                 _stream()), "rowstats_cast")
+    return (y, stats, shift) if with_shift else (y, stats)
 
 
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:

@@ -65,6 +65,13 @@ typedef struct blb_epilogue {
   float* stats_out;        /* or NULL */
   void* xb_out;            /* or NULL */
   int32_t ld_xb;
+  /* rolling per-row shift (ABI v3): xb, the statistics and the consumer's algebra live in "x - c_m" coordinates,
+   * c_m = the row mean one residual update ago, so the fold's rounding error no longer grows with |row mean| / row std.
+   *   producer (RESIDUAL): c_m = shift_in[m]; xb_out = bf16(x_new - c_m), stats_out = statistics of x_new - c_m;
+   *   folded consumer: algebra unchanged ((x-c) - mean(x-c) = x - mean(x)); it also writes the next producer's shift,
+   *   shift_out[m] = shift_in[m] + mean_m(x - c).  NULL: c = 0.  shift_in != shift_out (ping-pong buffers). */
+  const float* shift_in;   /* [M] or NULL */
+  float* shift_out;        /* [M] or NULL (folded consumer only) */
 } blb_epilogue;
 
 /* One timm `Block` (vision_transformer.Block as instantiated at dinosiglip_vit.py:50-58). */
@@ -144,9 +151,10 @@ int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
                   const blb_epilogue* epi, void* stream);
 /* partial-statistics pairs per row that a BLB_EPI_RESIDUAL launch with this N writes to stats_out (0: N unsupported) */
 int blb_gemm_stats_parts(int N);
-/* fp32 rows -> bf16 copy + (sum, sum of squares) in pair 0 of `parts` pairs per row (others zero): primes the folded chain */
+/* primes the folded chain: per row c = mean(x) -> shift[row] (shift == NULL: c = 0), bf16 copy of x - c, and the
+ * (sum, sum of squares) of x - c in pair 0 of `parts` pairs per row (others zero) */
 int blb_rowstats_cast(const float* x, int ldx, void* y_bf16, int ldy, float* stats, int parts, int rows, int D,
-                      void* stream);
+                      float* shift, void* stream);
 /* timm LayerNorm(D, eps) on fp32 rows -> bf16 rows (Block.norm1 / norm2). */
 int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void* y_bf16, int ldy, int rows, int D,
                   float eps, void* stream);

@@ -11,12 +11,12 @@ from .pipeline import PrefixGatherer, VisualPrefixEncoder, gather_prefixes, shar
 from .projector import FusedMLPProjector, PrismaticProjector
 from .vision import (DinoSigLIPImageTransform, DinoSigLIPViTBackbone, DinoV2ViTBackbone, PrismaticImageProcessor,
                      PrismaticVisionBackbone, SigLIPViTBackbone, VisionBackbone, VisionTransformer)
-from .vla import OpenVLA, OpenVLAForActionPrediction, PurePromptBuilder, decode_tail_from_logits
+from .vla import LLMBackbone, OpenVLA, OpenVLAForActionPrediction, PurePromptBuilder, decode_tail_from_logits
 
 __all__ = [
     "ActionTokenizer", "DINOV2_L14_REG4", "SIGLIP_SO400M_14", "VitConfig", "FUSED_DIM", "LLM_DIM",
     "fused_flops_per_image", "VisualPrefixEncoder", "PrefixGatherer", "gather_prefixes", "shard_bounds", "shard_pixel_values",
     "FusedMLPProjector", "PrismaticProjector", "DinoSigLIPImageTransform", "DinoSigLIPViTBackbone",
     "DinoV2ViTBackbone", "SigLIPViTBackbone", "PrismaticImageProcessor", "PrismaticVisionBackbone", "VisionBackbone", "VisionTransformer",
-    "OpenVLA", "OpenVLAForActionPrediction", "PurePromptBuilder", "decode_tail_from_logits",
+    "LLMBackbone", "OpenVLA", "OpenVLAForActionPrediction", "PurePromptBuilder", "decode_tail_from_logits",
 ]

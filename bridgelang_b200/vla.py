@@ -53,30 +53,157 @@ class PurePromptBuilder:
         return self.prompt.removeprefix(self.bos).rstrip()
 
 
-class OpenVLA(nn.Module):
-    def __init__(self, vision_backbone: nn.Module, projector: nn.Module, llm: nn.Module, tokenizer: Any,
-                 norm_stats: Dict[str, Dict[str, Dict[str, List[float]]]],
-                 action_tokenizer: Optional[ActionTokenizer] = None, empty_token_id: int = 29871) -> None:
-        super().__init__()
-        self.vision_backbone, self.projector, self.llm = vision_backbone, projector, llm
-        self.tokenizer = tokenizer
-        self.norm_stats = norm_stats
-        self.action_tokenizer = action_tokenizer if action_tokenizer is not None else ActionTokenizer(tokenizer)
-        self.prefix_encoder = VisualPrefixEncoder(vision_backbone, projector)
-        self.empty_token_id = empty_token_id
+class LLMBackbone(nn.Module):
+    """What this path needs of prismatic/models/backbones/llm/base_llm.py::LLMBackbone (the LLM itself is out of
+    scope and is driven as a black box): `.llm` (an HF-style causal LM), `.tokenizer` / `get_tokenizer()`, `.embed_dim`,
+    `.half_precision_dtype`, `.prompt_builder_fn`, `.identifier`."""
 
-    def get_prompt_builder(self) -> PurePromptBuilder:
-        return PurePromptBuilder("openvla")
+    def __init__(self, llm_backbone_id: str, llm: nn.Module, tokenizer: Any,
+                 half_precision_dtype: torch.dtype = torch.bfloat16) -> None:
+        super().__init__()
+        self.identifier = llm_backbone_id
+        self.llm = llm
+        self.tokenizer = tokenizer
+        self._half_precision_dtype = half_precision_dtype
+
+    def get_tokenizer(self):
+        return self.tokenizer
+
+    @property
+    def embed_dim(self) -> int:
+        return int(self.llm.config.hidden_size)
+
+    @property
+    def half_precision_dtype(self) -> torch.dtype:
+        return self._half_precision_dtype
+
+    @property
+    def prompt_builder_fn(self):
+        return PurePromptBuilder
+
+
+def _is_llama_tokenizer_fast(tokenizer: Any) -> bool:
+    try:
+        from transformers import LlamaTokenizerFast
+    except Exception:                               # transformers absent: nothing can be a LlamaTokenizerFast
+        return False
+    return isinstance(tokenizer, LlamaTokenizerFast)
+
+
+class OpenVLA(nn.Module):
+    """prismatic/models/vlas/openvla.py:23-33 on top of prismatic/models/vlms/prismatic.py:40-92 — same construction:
+
+        OpenVLA(model_id, vision_backbone, llm_backbone, enable_mixed_precision_training=True, arch_specifier=...,
+                norm_stats=..., action_tokenizer=...)
+        OpenVLA.from_pretrained(checkpoint_pt, model_id, vision_backbone, llm_backbone, arch_specifier=...,
+                                freeze_weights=True, norm_stats=..., action_tokenizer=...)      # load.py:214-224
+
+    `vision_backbone` is a (native) VisionBackbone, `llm_backbone` anything with the LLMBackbone contract above.  The
+    projector is built from `arch_specifier` exactly where the reference builds it (prismatic.py:60-68); this path
+    implements the fused three-layer projector, i.e. every `*fused-gelu-mlp` specifier (OpenVLA's is
+    `no-align+fused-gelu-mlp`) — `linear` / `gelu-mlp` raise.  `from_components` assembles the same object from an
+    already built projector and a bare HF causal LM (tests, the HF twin)."""
+
+    def __init__(self, model_id: str, vision_backbone: nn.Module, llm_backbone: nn.Module,
+                 enable_mixed_precision_training: bool = True, arch_specifier: str = "gelu-mlp", *,
+                 norm_stats: Dict[str, Dict[str, Dict[str, List[float]]]], action_tokenizer: ActionTokenizer,
+                 empty_token_id: int = 29871, **kwargs: Any) -> None:
+        super().__init__()
+        from .projector import FusedMLPProjector
+        self.model_family, self.model_id = "prismatic", model_id
+        self.vision_backbone, self.llm_backbone = vision_backbone, llm_backbone
+        self.enable_mixed_precision_training = enable_mixed_precision_training
+        torch.manual_seed(vision_backbone.embed_dim)            # prismatic.py:57 (projector init consistency)
+        self.arch_specifier = arch_specifier
+        if arch_specifier.endswith("fused-gelu-mlp"):
+            self.projector = FusedMLPProjector(vision_backbone.embed_dim, llm_backbone.embed_dim)
+        elif arch_specifier == "linear" or arch_specifier.endswith("gelu-mlp"):
+            raise ValueError(f"PrismaticVLM with `{arch_specifier = }` is not on the B200-native path (it implements "
+                             f"the fused three-layer projector of the fused DINOv2+SigLIP backbones)")
+        else:
+            raise ValueError(f"PrismaticVLM with `{arch_specifier = }` is not supported!")
+        self.vision_backbone_requires_grad = False
+        self.all_module_keys = ["vision_backbone", "llm_backbone", "projector"]
+        self.trainable_module_keys: List[str] = []
+        self.norm_stats = norm_stats
+        self.action_tokenizer = action_tokenizer
+        self.empty_token_id = empty_token_id
+        self._prefix_encoder: Optional[VisualPrefixEncoder] = None
+
+    # -- construction paths ------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_checkpoint, model_id: str, vision_backbone: nn.Module, llm_backbone: nn.Module,
+                        enable_mixed_precision_training: bool = True, arch_specifier: str = "gelu-mlp",
+                        freeze_weights: bool = True, **kwargs: Any) -> "OpenVLA":
+        """prismatic.py:85-123: build, then load `["model"]["projector" | "llm_backbone" | ("vision_backbone")]`."""
+        vlm = cls(model_id, vision_backbone, llm_backbone, enable_mixed_precision_training=enable_mixed_precision_training,
+                  arch_specifier=arch_specifier, **kwargs)
+        model_state_dict = torch.load(pretrained_checkpoint, map_location="cpu")["model"]
+        assert (
+            "projector" in model_state_dict and "llm_backbone" in model_state_dict
+        ), "PrismaticVLM `from_pretrained` expects checkpoint with keys for `projector` AND `llm_backbone`!"
+        vlm.projector.load_state_dict(model_state_dict["projector"])
+        vlm.llm_backbone.load_state_dict(model_state_dict["llm_backbone"])
+        if "vision_backbone" in model_state_dict.keys():
+            vlm.vision_backbone.load_state_dict(model_state_dict["vision_backbone"])
+        if freeze_weights:
+            vlm.requires_grad_(False)
+            vlm.eval()
+        return vlm
+
+    @classmethod
+    def from_components(cls, vision_backbone: nn.Module, projector: nn.Module, llm: nn.Module, tokenizer: Any,
+                        norm_stats: Dict, action_tokenizer: Optional[ActionTokenizer] = None,
+                        model_id: str = "openvla", llm_backbone_id: str = "llama2-7b-pure") -> "OpenVLA":
+        backbone = llm if isinstance(llm, LLMBackbone) else LLMBackbone(llm_backbone_id, llm, tokenizer)
+        vla = cls.__new__(cls)
+        nn.Module.__init__(vla)
+        vla.model_family, vla.model_id = "prismatic", model_id
+        vla.vision_backbone, vla.llm_backbone, vla.projector = vision_backbone, backbone, projector
+        vla.enable_mixed_precision_training, vla.arch_specifier = True, "no-align+fused-gelu-mlp"
+        vla.vision_backbone_requires_grad = False
+        vla.all_module_keys, vla.trainable_module_keys = ["vision_backbone", "llm_backbone", "projector"], []
+        vla.norm_stats = norm_stats
+        vla.action_tokenizer = action_tokenizer if action_tokenizer is not None else ActionTokenizer(tokenizer)
+        vla.empty_token_id = 29871
+        vla._prefix_encoder = None
+        return vla
+
+    # -- reference attribute names -----------------------------------------------------------------------
+    @property
+    def llm(self) -> nn.Module:
+        return self.llm_backbone.llm
+
+    @property
+    def tokenizer(self):
+        return self.llm_backbone.tokenizer
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.llm.parameters()).device
+
+    @property
+    def prefix_encoder(self) -> VisualPrefixEncoder:
+        if self._prefix_encoder is None:
+            object.__setattr__(self, "_prefix_encoder", VisualPrefixEncoder(self.vision_backbone, self.projector))
+        return self._prefix_encoder
+
+    def get_prompt_builder(self, system_prompt: Optional[str] = None) -> PurePromptBuilder:
+        return self.llm_backbone.prompt_builder_fn("prismatic", system_prompt=system_prompt)
 
     # -- the part of predict_action between the tokenizer and generate() --------------------------------
     def _prepare_input_ids(self, instruction: str, device: torch.device) -> torch.Tensor:
+        tokenizer = self.llm_backbone.tokenizer
         prompt_builder = self.get_prompt_builder()
         prompt_builder.add_turn(role="human", message=f"What action should the robot take to {instruction.lower()}?")
         prompt_text = prompt_builder.get_prompt()
-        input_ids = self.tokenizer(prompt_text, truncation=True, return_tensors="pt").input_ids.to(device)
-        if not torch.all(input_ids[:, -1] == self.empty_token_id):   # openvla.py:59-64
-            extra = torch.tensor([[self.empty_token_id]], dtype=torch.long, device=device)
-            input_ids = torch.cat((input_ids, extra), dim=1)
+        input_ids = tokenizer(prompt_text, truncation=True, return_tensors="pt").input_ids.to(device)
+        if _is_llama_tokenizer_fast(tokenizer):                      # openvla.py:57-66
+            if not torch.all(input_ids[:, -1] == self.empty_token_id):
+                extra = torch.tensor([[self.empty_token_id]], dtype=torch.long, device=device)
+                input_ids = torch.cat((input_ids, extra), dim=1)
+        else:
+            raise ValueError(f"Unsupported `tokenizer` type = {type(tokenizer)}")
         return input_ids
 
     @torch.inference_mode()
@@ -102,10 +229,26 @@ class OpenVLA(nn.Module):
                 out = self.llm(inputs_embeds=emb(nxt.view(1, 1)), past_key_values=out.past_key_values, use_cache=True)
         return torch.cat(ids)
 
+    # generate() arguments the greedy device loop honours (everything else the reference would forward to
+    # GenerationMixin.generate is rejected instead of being dropped on the floor)
+    _GENERATE_KWARGS = {"do_sample": False, "use_cache": None, "num_beams": 1, "temperature": None, "top_p": None,
+                        "top_k": None, "pad_token_id": None, "eos_token_id": None}
+
+    @classmethod
+    def _check_generate_kwargs(cls, kwargs: Dict[str, Any]) -> None:
+        for k, v in kwargs.items():
+            if k not in cls._GENERATE_KWARGS:
+                raise ValueError(f"predict_action: unsupported generate() argument `{k}` on the native greedy decode path")
+            want = cls._GENERATE_KWARGS[k]
+            if want is not None and v is not None and v != want:
+                raise ValueError(f"predict_action: `{k}={v}` is not supported (the native decode tail is greedy: "
+                                 f"`{k}={want}`, as the reference's scripts run it)")
+
     @torch.inference_mode()
     def predict_action(self, image, instruction: str, unnorm_key: Optional[str] = None, **kwargs: str) -> np.ndarray:
         """PIL image + instruction → un-normalized continuous action, np.float64[action_dim]."""
-        device = next(self.llm.parameters()).device
+        self._check_generate_kwargs(kwargs)
+        device = self.device
         input_ids = self._prepare_input_ids(instruction, device)
         pixel_values = self.vision_backbone.get_image_transform()(image)
         if isinstance(pixel_values, torch.Tensor):
@@ -170,8 +313,8 @@ class OpenVLAForActionPrediction(nn.Module):
         self._action_tokenizer = ActionTokenizer(_Vocab(), bins=n_action_bins)
         # shares the greedy loop with the native class; kept out of the module tree so that state_dict() has the
         # reference's keys only (vision_backbone.*, projector.*, language_model.*)
-        object.__setattr__(self, "_core", OpenVLA(vision_backbone, projector, language_model, _Vocab(), norm_stats,
-                                                  self._action_tokenizer))
+        object.__setattr__(self, "_core", OpenVLA.from_components(vision_backbone, projector, language_model, _Vocab(),
+                                                                  norm_stats, self._action_tokenizer))
 
     @torch.inference_mode()
     def predict_action(self, input_ids: Optional[torch.LongTensor] = None, unnorm_key: Optional[str] = None,
@@ -179,8 +322,7 @@ class OpenVLAForActionPrediction(nn.Module):
         pixel_values = kwargs.get("pixel_values")
         if input_ids is None or pixel_values is None:
             raise ValueError("predict_action needs `input_ids` and `pixel_values` (the processor's outputs)")
-        if kwargs.get("do_sample", False):
-            raise ValueError("the native decode tail is greedy (the reference calls generate with do_sample=False)")
+        OpenVLA._check_generate_kwargs({k: v for k, v in kwargs.items() if k not in ("pixel_values", "attention_mask")})
         if not torch.all(input_ids[:, -1] == 29871):                      # modeling_prismatic.py:512-515
             input_ids = torch.cat(
                 (input_ids, torch.unsqueeze(torch.Tensor([29871]).long(), dim=0).to(input_ids.device)), dim=1)

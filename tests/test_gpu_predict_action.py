@@ -20,9 +20,17 @@ STATS = {"bridge_orig": {"action": {"q01": [-0.03, -0.04, -0.05, -0.08, -0.10, -
                                     "mask": [True] * 6 + [False]}}}
 
 
-class _Tok:
-    """Llama-tokenizer stand-in: deterministic ids in [3, 31000), BOS=1 first, vocab_size 32000."""
+from transformers import LlamaTokenizerFast  # noqa: E402
+
+
+class _Tok(LlamaTokenizerFast):
+    """Llama-tokenizer stand-in: deterministic ids in [3, 31000), BOS=1 first, vocab_size 32000.  It IS-A
+    LlamaTokenizerFast because predict_action, like the reference (openvla.py:57-66), refuses anything else; no tokenizer
+    files exist offline, so the base constructor is bypassed."""
     vocab_size = 32000
+
+    def __init__(self):
+        pass
 
     def __call__(self, text, truncation=True, return_tensors="pt"):
         ids = [1] + [3 + (sum(map(ord, w)) * 7919) % 30000 for w in text.split()]
@@ -48,7 +56,15 @@ def vla():
     proj = blb.FusedMLPProjector(2176, 4096)
     proj.load_state_dict(make_projector_state_dict(seed=3))
     bb.cuda(), proj.cuda()
-    return blb.OpenVLA(bb, proj, llm, _Tok(), STATS)
+    # the reference's construction path (openvla.py:23-33 / load.py:214-224): model_id, vision_backbone, llm_backbone,
+    # arch_specifier; norm_stats + action_tokenizer by keyword; the projector is built inside and then loaded
+    llm_backbone = blb.LLMBackbone("llama2-7b-pure", llm, _Tok())
+    vla = blb.OpenVLA("openvla-test", bb, llm_backbone, arch_specifier="no-align+fused-gelu-mlp", norm_stats=STATS,
+                      action_tokenizer=blb.ActionTokenizer(llm_backbone.get_tokenizer()))
+    vla.projector.load_state_dict(proj.state_dict())
+    vla.projector.cuda()
+    assert vla.llm is llm and vla.tokenizer is llm_backbone.tokenizer and vla.model_id == "openvla-test"
+    return vla
 
 
 def test_predict_action_matches_reference_style_pipeline(vla):
@@ -100,6 +116,23 @@ def test_unnorm_key_errors(vla):
     img = Image.fromarray(np.zeros((224, 224, 3), dtype=np.uint8))
     with pytest.raises(AssertionError, match="not in the set of available statistics"):
         vla.predict_action(img, "do something", unnorm_key="no_such_dataset")
+    # generate() arguments: greedy ones are accepted, anything else is rejected instead of silently ignored
+    a = vla.predict_action(img, "do something", do_sample=False, use_cache=True)
+    assert a.shape == (7,)
+    with pytest.raises(ValueError, match="do_sample"):
+        vla.predict_action(img, "do something", do_sample=True)
+    with pytest.raises(ValueError, match="unsupported generate"):
+        vla.predict_action(img, "do something", repetition_penalty=1.2)
+    # the reference refuses tokenizers that are not LlamaTokenizerFast (openvla.py:66)
+    class _Other:
+        vocab_size = 32000
+        def __call__(self, text, truncation=True, return_tensors="pt"):
+            class _Out:
+                input_ids = torch.tensor([[1, 5, 6]], dtype=torch.long)
+            return _Out()
+    other = blb.OpenVLA.from_components(vla.vision_backbone, vla.projector, vla.llm, _Other(), STATS)
+    with pytest.raises(ValueError, match="Unsupported `tokenizer` type"):
+        other.predict_action(img, "do something")
 
 
 def test_hf_twin_predict_action_equals_native(vla):

@@ -256,3 +256,66 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_openvla_reference_construction_and_from_pretrained(tmp_path):
+    """openvla.py:23-33 + prismatic.py:40-123 + load.py:214-224: OpenVLA(model_id, vision_backbone, llm_backbone,
+    arch_specifier=..., norm_stats=..., action_tokenizer=...) builds the projector from the arch specifier;
+    from_pretrained loads ["model"]["projector" | "llm_backbone" | "vision_backbone"] and freezes."""
+    import torch.nn as nn
+
+    class _Cfg:
+        hidden_size = 64
+
+    class _TinyLM(nn.Module):
+        config = _Cfg()
+
+        def __init__(self):
+            super().__init__()
+            self.emb = nn.Embedding(10, 64)
+
+    class _Tok:
+        vocab_size = 32000
+
+    stats = {"bridge_orig": {"action": {"q01": [0.0] * 7, "q99": [1.0] * 7}}}
+    dcfg, scfg = DINOV2_L14_REG4.with_depth(2), SIGLIP_SO400M_14.with_depth(2)
+
+    def backbone():
+        bb = blb.DinoSigLIPViTBackbone("dinosiglip-vit-so-224px", "resize-naive")
+        bb.dino_featurizer, bb.siglip_featurizer = blb.VisionTransformer(dcfg), blb.VisionTransformer(scfg)
+        return bb
+
+    src_bb = backbone()
+    src_bb.dino_featurizer.load_state_dict(make_vit_state_dict(dcfg, seed=5))
+    src_bb.siglip_featurizer.load_state_dict(make_vit_state_dict(scfg, seed=6))
+    llm_backbone = blb.LLMBackbone("llama2-7b-pure", _TinyLM(), _Tok())
+    assert llm_backbone.embed_dim == 64 and llm_backbone.half_precision_dtype == torch.bfloat16
+    at = blb.ActionTokenizer(llm_backbone.get_tokenizer())
+    src = blb.OpenVLA("openvla-7b", src_bb, llm_backbone, arch_specifier="no-align+fused-gelu-mlp", norm_stats=stats,
+                      action_tokenizer=at)
+    assert isinstance(src.projector, blb.FusedMLPProjector) and src.projector.projector[0].in_features == 2176
+    assert src.projector.projector[4].out_features == 64
+    assert src.all_module_keys == ["vision_backbone", "llm_backbone", "projector"] and src.model_family == "prismatic"
+    assert src.get_action_dim() == 7 and src.norm_stats is stats and src.action_tokenizer is at
+    for bad in ("linear", "gelu-mlp", "something-else"):
+        with pytest.raises(ValueError):
+            blb.OpenVLA("x", src_bb, llm_backbone, arch_specifier=bad, norm_stats=stats, action_tokenizer=at)
+    with pytest.raises(TypeError):                       # norm_stats / action_tokenizer are required keywords
+        blb.OpenVLA("x", src_bb, llm_backbone, arch_specifier="fused-gelu-mlp")
+    ckpt = tmp_path / "step-000001.pt"
+    torch.save({"model": {"projector": src.projector.state_dict(), "llm_backbone": llm_backbone.state_dict(),
+                          "vision_backbone": src_bb.state_dict()}}, ckpt)
+    dst = blb.OpenVLA.from_pretrained(ckpt, "openvla-7b", backbone(), blb.LLMBackbone("llama2-7b-pure", _TinyLM(), _Tok()),
+                                      arch_specifier="no-align+fused-gelu-mlp", freeze_weights=True, norm_stats=stats,
+                                      action_tokenizer=at)
+    assert not any(p.requires_grad for p in dst.parameters()) and not dst.training
+    for (ka, va), (kb, vb) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    torch.save({"model": {"projector": src.projector.state_dict()}}, ckpt)
+    with pytest.raises(AssertionError, match="expects checkpoint with keys"):
+        blb.OpenVLA.from_pretrained(ckpt, "m", backbone(), llm_backbone, arch_specifier="fused-gelu-mlp",
+                                    norm_stats=stats, action_tokenizer=at)
+    # generate() kwargs policy is host logic
+    blb.OpenVLA._check_generate_kwargs({"do_sample": False, "use_cache": False})
+    with pytest.raises(ValueError):
+        blb.OpenVLA._check_generate_kwargs({"num_beams": 4})

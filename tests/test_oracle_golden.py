@@ -126,3 +126,30 @@ def test_tower_oracle_against_frozen_hf_outputs(golden_dir):
         assert ((got[0, ::8, ::16] - ref).abs().max() / scale).item() < 2e-5, name
         assert abs(got.double().sum().item() - float(g[f"{name}_sum"])) < 1e-4 * float(g[f"{name}_abs_sum"])
         assert abs(got.double().abs().sum().item() / float(g[f"{name}_abs_sum"]) - 1) < 1e-5
+
+
+def test_tower_oracle_against_frozen_hf_outputs_full_depth_batch2(golden_dir):
+    """Round 2 (VERDICT r01 "next" 1e): the same pin at the depth the product runs — 24 / 27 blocks, the weights of the
+    parity gates (seeds 1234 / 1235, stress-init) and a batch of two frames — against transformers' independent
+    implementations frozen in tests/golden/hf_towers_full_depth.npz.  The GPU parity tests compare the kernels with this
+    very oracle on these very weights, so the chain  kernels == oracle == HF  closes at full depth."""
+    import numpy as np
+    import torch
+    from bridgelang_b200.config import DINOV2_L14_REG4, SIGLIP_SO400M_14
+    from bridgelang_b200.weights import make_vit_state_dict
+    from oracle import vit_oracle
+
+    g = np.load(golden_dir / "hf_towers_full_depth.npz")
+    for name, cfg in (("dino", DINOV2_L14_REG4), ("siglip", SIGLIP_SO400M_14)):
+        assert int(g[f"{name}_depth"]) == cfg.depth
+        sd = make_vit_state_dict(cfg, seed=int(g[f"{name}_weight_seed"]), init="stress")
+        x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(int(g[f"{name}_pixel_seed"])))
+        with torch.no_grad():
+            got = vit_oracle.vit_intermediate(sd, cfg, x)
+        ref = torch.from_numpy(g[f"{name}_slice"])
+        assert got.shape == (2, 256, cfg.dim) and ref.shape == got[:, ::8, ::16].shape
+        assert ((got[:, ::8, ::16] - ref).abs().max() / ref.abs().max()).item() < 5e-5, name
+        assert abs(got.double().sum().item() - float(g[f"{name}_sum"])) < 1e-4 * float(g[f"{name}_abs_sum"])
+        assert abs(got.double().abs().sum().item() / float(g[f"{name}_abs_sum"]) - 1) < 1e-5
+        # the two images differ (a batch-index bug would not hide behind identical frames)
+        assert (ref[0] - ref[1]).abs().max() > 0.05 * ref.abs().max()

@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 # BLB_LIB: development override (A/B of two builds on one box); the product path is the in-tree library
 LIB_PATH = Path(os.environ["BLB_LIB"]) if os.environ.get("BLB_LIB") else PKG_DIR / "libbridgelang_b200.so"
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_PATCH, EPI_BIAS_QGELU = 0, 1, 2, 3, 4
 DTYPE_F32, DTYPE_BF16, DTYPE_F16, DTYPE_F64 = 0, 1, 2, 3
 
 c_f32p = C.POINTER(C.c_float)
@@ -44,7 +44,8 @@ class VitWeights(C.Structure):
         ("n_prefix", C.c_int32), ("n_blocks", C.c_int32), ("patch_ldk", C.c_int32), ("ln_eps", C.c_float),
         ("patch_w", C.c_void_p), ("patch_b", C.c_void_p), ("pos_embed", C.c_void_p), ("prefix", C.c_void_p),
         ("blocks_host", C.POINTER(BlockWeights)), ("ln_folded", C.c_int32),
-        ("hidden", C.c_int32),
+        ("hidden", C.c_int32), ("grid", C.c_int32), ("img_size", C.c_int32), ("act", C.c_int32),
+        ("norm_pre_w", C.c_void_p), ("norm_pre_b", C.c_void_p), ("patch_w_u8", C.c_void_p), ("patch_b_u8", C.c_void_p),
     ]
 
 
@@ -77,7 +78,16 @@ _SIGNATURES = {
                                 C.c_float, C.c_void_p]),
     "blb_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "blb_im2col_patch14": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "blb_u8_to_patches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "blb_resize_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "blb_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitWeights), C.c_int]),
+    "blb_vit_tower_forward_u8": (C.c_int, [C.POINTER(VitWeights), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    "blb_patch_matrix_bytes": (C.c_size_t, [C.POINTER(VitWeights), C.c_int]),
+    "blb_fused_featurize_project_forward_u8": (C.c_int, [C.POINTER(VitWeights), C.POINTER(VitWeights),
+                                                         C.POINTER(ProjectorWeights), C.c_void_p, C.c_int, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "blb_vit_tower_forward": (C.c_int, [C.POINTER(VitWeights), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "blb_projector_workspace_bytes": (C.c_size_t, [C.POINTER(ProjectorWeights), C.c_int]),

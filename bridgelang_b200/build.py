@@ -19,7 +19,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 BUILD_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libbridgelang_b200.so"
-SOURCES = ["gemm_tcgen05.cu", "layernorm.cu", "attention.cu", "attention_tc.cu", "patch_embed.cu", "decode_tail.cu", "capi.cu"]
+SOURCES = ["gemm_tcgen05.cu", "layernorm.cu", "attention.cu", "attention_tc.cu", "patch_embed.cu", "resize.cu", "decode_tail.cu", "capi.cu"]
 HEADERS = [CSRC / "ptx.cuh", CSRC / "gemm.h", PKG_DIR.parent / "include" / "bridgelang_b200.h"]
 
 # BLB_NVCC_EXTRA: extra nvcc flags for development builds (e.g. "-DBLB_ATTN_POLY_MASK=0"), part of the build digest

@@ -17,7 +17,9 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bfloat16*>(p); }
 inline __nv_bfloat16* bf(void* p) { return static_cast<__nv_bfloat16*>(p); }
 
-constexpr int PATCHES = 256;  // 224 / 14 squared
+inline int grid_of(const blb_vit_weights* w) { return w->grid > 0 ? w->grid : 16; }          // 224 / 14
+inline int patches_of(const blb_vit_weights* w) { return grid_of(w) * grid_of(w); }
+inline int img_of(const blb_vit_weights* w) { return w->img_size > 0 ? w->img_size : 14 * grid_of(w); }
 const bool g_serpentine = getenv("BLB_NO_SERPENTINE") == nullptr;   // A/B switch for the L2-aware row order
 
 struct TowerWs {
@@ -29,7 +31,7 @@ struct TowerWs {
 // LN-folded towers add: xb bf16 [M,D] (bf16 copy of the residual stream = A operand of qkv / fc1) and
 // stats float2 [M, parts] (per-row partial sums written by the proj / fc2 epilogues)
 TowerWs tower_ws(const blb_vit_weights* w, int batch) {
-  const size_t T = PATCHES + w->n_prefix, M = static_cast<size_t>(batch) * T, D = w->dim;
+  const size_t T = patches_of(w) + w->n_prefix, M = static_cast<size_t>(batch) * T, D = w->dim;
   const size_t wide = std::max<size_t>(std::max<size_t>(3 * D, w->hidden_pad), w->patch_ldk);
   TowerWs s;
   s.resid = 0;
@@ -44,9 +46,11 @@ TowerWs tower_ws(const blb_vit_weights* w, int batch) {
 }
 
 int check_vit(const blb_vit_weights* w) {
-  if (w == nullptr || w->blocks_host == nullptr || w->patch_w == nullptr || w->patch_b == nullptr ||
-      w->pos_embed == nullptr)
+  if (w == nullptr || w->blocks_host == nullptr || w->patch_w == nullptr || w->pos_embed == nullptr)
     return BLB_ERR_ARG;
+  if (w->grid < 0 || w->grid > 64 || (w->act != 0 && w->act != 1)) return BLB_ERR_ARG;
+  if (w->img_size != 0 && w->img_size < 14 * grid_of(w)) return BLB_ERR_ARG;
+  if ((w->norm_pre_w == nullptr) != (w->norm_pre_b == nullptr)) return BLB_ERR_ARG;
   if (w->dim != w->heads * w->head_dim || w->n_blocks <= 0 || w->n_prefix < 0) return BLB_ERR_ARG;
   if (w->n_prefix > 0 && w->prefix == nullptr) return BLB_ERR_ARG;
   if (w->dim % 128 != 0 || w->hidden_pad % 128 != 0 || w->patch_ldk % 8 != 0 || w->patch_ldk < 588)
@@ -100,8 +104,10 @@ TowerOverlap* tower_overlap_ctx() {
 int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int ld_out, int out_col_off, float* resid,
                            __nv_bfloat16* attn, __nv_bfloat16* big, __nv_bfloat16* xb, float2* stats,
                            float* shift2[2], cudaStream_t st) {
+  const int PATCHES = patches_of(w);
   const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
   const double Hreal = w->hidden > 0 ? w->hidden : w->hidden_pad;   // algorithmic (unpadded) MLP width
+  const int fc1_mode = w->act == 1 ? EPI_BIAS_QGELU : EPI_BIAS_GELU;
   const int parts = gemm_stats_parts(D);
   if (parts <= 0) return BLB_ERR_SHAPE;
   // xb, the statistics and the consumers' algebra all live in "x minus a per-row shift" coordinates; the shift is the
@@ -162,7 +168,7 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
       consumer(e);
       e.alg_work = 2.0 * M * Hreal * D;
       e.reverse = next_dir();
-      BLB_TRY(gemm_bf16(xb, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
+      BLB_TRY(gemm_bf16(xb, D, bf(b.fc1_w), D, M, Hm, D, fc1_mode, e, st));
     }
     {
       GemmEpilogue e;
@@ -188,24 +194,34 @@ int tower_blocks_ln_folded(const blb_vit_weights* w, int batch, void* out, int l
   return 0;
 }
 
+// `pixels`: normalized bf16 [batch,3,S,S] (im2col here), or — u8_patches != nullptr — the shared uint8 patch matrix
+// [batch*grid², patch_ldk] built by u8_to_patches (then the folded patch_w_u8 / patch_b_u8 are the GEMM operands)
 int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void* out, int ld_out, int out_col_off,
-                  void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                  void* workspace, size_t workspace_bytes, cudaStream_t st, const __nv_bfloat16* u8_patches = nullptr) {
   BLB_TRY(check_vit(w));
-  if (pixels == nullptr || out == nullptr || workspace == nullptr || batch <= 0) return BLB_ERR_ARG;
+  if ((pixels == nullptr && u8_patches == nullptr) || out == nullptr || workspace == nullptr || batch <= 0)
+    return BLB_ERR_ARG;
+  if (u8_patches != nullptr && (w->patch_w_u8 == nullptr || w->patch_b_u8 == nullptr)) return BLB_ERR_ARG;
   const TowerWs ws = tower_ws(w, batch);
   if (workspace_bytes < ws.total) return BLB_ERR_WORKSPACE;
   uint8_t* base = static_cast<uint8_t*>(workspace);
   float* resid = reinterpret_cast<float*>(base + ws.resid);
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(base + ws.xn);
   __nv_bfloat16* big = reinterpret_cast<__nv_bfloat16*>(base + ws.big);
+  const int PATCHES = patches_of(w);
   const int D = w->dim, T = PATCHES + w->n_prefix, M = batch * T, Hm = w->hidden_pad;
   const double Hreal = w->hidden > 0 ? w->hidden : w->hidden_pad;   // algorithmic (unpadded) MLP width
+  const int fc1_mode = w->act == 1 ? EPI_BIAS_QGELU : EPI_BIAS_GELU;
 
   // --- PatchEmbed (+bias +pos_embed) and the cls/reg prefix rows: timm patch_embed + _pos_embed ---------
-  BLB_TRY(im2col_patch14(bf(pixels), big, batch, w->patch_ldk, st));
+  const __nv_bfloat16* patch_a = u8_patches;
+  if (patch_a == nullptr) {
+    BLB_TRY(im2col_patch14(bf(pixels), big, batch, w->patch_ldk, st, grid_of(w), img_of(w)));
+    patch_a = big;
+  }
   {
     GemmEpilogue e;
-    e.bias = w->patch_b;
+    e.bias = u8_patches != nullptr ? w->patch_b_u8 : w->patch_b;
     e.pos = w->pos_embed;
     e.resid = resid;
     e.ld_resid = D;
@@ -213,10 +229,12 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
     e.tok_out = T;
     e.tok_shift = w->n_prefix;
     e.alg_work = 2.0 * batch * PATCHES * D * 588.0;   // K = 3·14·14; patch_ldk only pads the row pitch
-    BLB_TRY(gemm_bf16(big, w->patch_ldk, bf(w->patch_w), w->patch_ldk, batch * PATCHES, D, w->patch_ldk, EPI_PATCH, e,
-                      st));
+    BLB_TRY(gemm_bf16(patch_a, w->patch_ldk, bf(u8_patches != nullptr ? w->patch_w_u8 : w->patch_w), w->patch_ldk,
+                      batch * PATCHES, D, w->patch_ldk, EPI_PATCH, e, st));
   }
   BLB_TRY(write_prefix_tokens(w->prefix, resid, batch, T, w->n_prefix, D, st));
+  if (w->norm_pre_w != nullptr)   // timm pre_norm (CLIP): x = norm_pre(x) on every token, in place on the fp32 stream
+    BLB_TRY(layernorm_f32_f32(resid, D, w->norm_pre_w, w->norm_pre_b, resid, D, M, D, w->ln_eps, st));
   if (w->ln_folded) {
     float* shift2[2] = {reinterpret_cast<float*>(base + ws.shift),
                         reinterpret_cast<float*>(base + ws.shift + ws.shift_bytes)};
@@ -261,7 +279,7 @@ int tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void*
       e.ld_out = Hm;
       e.alg_work = 2.0 * M * Hreal * D;
       e.reverse = r_mm;
-      BLB_TRY(gemm_bf16(xn, D, bf(b.fc1_w), D, M, Hm, D, EPI_BIAS_GELU, e, st));
+      BLB_TRY(gemm_bf16(xn, D, bf(b.fc1_w), D, M, Hm, D, fc1_mode, e, st));
     }
     {
       GemmEpilogue e;
@@ -384,13 +402,13 @@ int blb_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, 
   e.shift_in = epi->shift_in;
   e.shift_out = epi->shift_out;
   if (e.xb_out != nullptr && e.ld_xb % 8 != 0) return BLB_ERR_ARG;
-  if (mode == EPI_BIAS || mode == EPI_BIAS_GELU) {
+  if (mode == EPI_BIAS || mode == EPI_BIAS_GELU || mode == EPI_BIAS_QGELU) {
     if (e.out == nullptr || e.ld_out % 8 != 0 || e.out_col_off % 8 != 0) return BLB_ERR_ARG;
   } else if (mode == EPI_RESIDUAL) {
     if (e.resid == nullptr || e.ld_resid % 4 != 0) return BLB_ERR_ARG;
     if (e.out != nullptr && (e.ld_out % 8 != 0 || e.out_col_off % 8 != 0)) return BLB_ERR_ARG;
   } else if (mode == EPI_PATCH) {
-    if (e.resid == nullptr || e.pos == nullptr || e.tok_in <= 0 || e.ld_resid % 4 != 0) return BLB_ERR_ARG;
+    if (e.resid == nullptr || e.tok_in <= 0 || e.ld_resid % 4 != 0) return BLB_ERR_ARG;
   } else {
     return BLB_ERR_ARG;
   }
@@ -420,7 +438,8 @@ int blb_im2col_patch14(const void* pixels, void* cols, int B, int ldk, void* str
 
 size_t blb_vit_workspace_bytes(const blb_vit_weights* w, int batch) {
   if (w == nullptr || batch <= 0) return 0;
-  return tower_ws(w, batch).total;
+  // + the uint8 entry's patch matrix when the tower has folded patch weights
+  return align_up(tower_ws(w, batch).total) + (w->patch_w_u8 != nullptr ? blb_patch_matrix_bytes(w, batch) : 0);
 }
 
 int blb_vit_tower_forward(const blb_vit_weights* w, const void* pixels, int batch, void* out, int ld_out,
@@ -447,17 +466,19 @@ size_t blb_fused_workspace_bytes(const blb_vit_weights* dino, const blb_vit_weig
   if (dino == nullptr || siglip == nullptr || batch <= 0) return 0;
   // the two towers may run concurrently (tower_overlap) → disjoint regions; the projector runs after both and aliases them
   size_t s = align_up(tower_ws(dino, batch).total) + tower_ws(siglip, batch).total;
-  if (proj != nullptr) s = std::max(s, projector_ws(proj, batch * PATCHES));
+  if (proj != nullptr) s = std::max(s, projector_ws(proj, batch * patches_of(dino)));
   return s;
 }
 
-int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_vit_weights* siglip,
-                                        const blb_projector_weights* proj, const void* pixels_dino,
-                                        const void* pixels_siglip, int batch, void* features, void* projected,
-                                        void* workspace, size_t workspace_bytes, void* stream) {
+namespace {
+int fused_forward(const blb_vit_weights* dino, const blb_vit_weights* siglip, const blb_projector_weights* proj,
+                  const void* pixels_dino, const void* pixels_siglip, const __nv_bfloat16* u8_patches, int batch,
+                  void* features, void* projected, void* workspace, size_t workspace_bytes, void* stream) {
   if (dino == nullptr || siglip == nullptr || features == nullptr) return BLB_ERR_ARG;
   if (proj != nullptr && projected == nullptr) return BLB_ERR_ARG;
+  if (patches_of(dino) != patches_of(siglip)) return BLB_ERR_SHAPE;   // the concat needs the same patch grid
   if (workspace_bytes < blb_fused_workspace_bytes(dino, siglip, proj, batch)) return BLB_ERR_WORKSPACE;
+  const int PATCHES = patches_of(dino);
   const int fused_dim = dino->dim + siglip->dim;
   if (proj != nullptr && proj->in_dim != fused_dim) return BLB_ERR_SHAPE;
   cudaStream_t st = as_stream(stream);
@@ -472,20 +493,73 @@ int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_v
   if (ov != nullptr) {
     BLB_CUDA(cudaEventRecord(ov->fork, st));
     BLB_CUDA(cudaStreamWaitEvent(ov->side, ov->fork, 0));
-    BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, dino_bytes, st));
+    BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, dino_bytes, st, u8_patches));
     BLB_TRY(tower_forward(siglip, pixels_siglip, batch, features, fused_dim, dino->dim, ws_siglip,
-                          workspace_bytes - dino_bytes, ov->side));
+                          workspace_bytes - dino_bytes, ov->side, u8_patches));
     BLB_CUDA(cudaEventRecord(ov->join, ov->side));
     BLB_CUDA(cudaStreamWaitEvent(st, ov->join, 0));
   } else {
-    BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, dino_bytes, st));
+    BLB_TRY(tower_forward(dino, pixels_dino, batch, features, fused_dim, 0, workspace, dino_bytes, st, u8_patches));
     BLB_TRY(tower_forward(siglip, pixels_siglip, batch, features, fused_dim, dino->dim, ws_siglip,
-                          workspace_bytes - dino_bytes, st));
+                          workspace_bytes - dino_bytes, st, u8_patches));
   }
   if (proj != nullptr)
     BLB_TRY(projector_forward(proj, features, fused_dim, batch * PATCHES, projected, proj->out_dim, 0, 0, 0, workspace,
                               workspace_bytes, st));
   return 0;
+}
+}  // namespace
+
+int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                        const blb_projector_weights* proj, const void* pixels_dino,
+                                        const void* pixels_siglip, int batch, void* features, void* projected,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (pixels_dino == nullptr || pixels_siglip == nullptr) return BLB_ERR_ARG;
+  return fused_forward(dino, siglip, proj, pixels_dino, pixels_siglip, nullptr, batch, features, projected, workspace,
+                       workspace_bytes, stream);
+}
+
+size_t blb_patch_matrix_bytes(const blb_vit_weights* w, int batch) {
+  if (w == nullptr || batch <= 0) return 0;
+  return align_up(static_cast<size_t>(batch) * patches_of(w) * w->patch_ldk * 2);
+}
+
+// One uint8 frame → ONE patch matrix (exact integers, HWC patch order) → the A operand of both towers' patch-embed GEMMs.
+// The matrix lives behind the towers' workspaces; it is written before the fork event, so the side stream sees it.
+int blb_fused_featurize_project_forward_u8(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                           const blb_projector_weights* proj, const uint8_t* frames_hwc, int batch,
+                                           void* features, void* projected, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  if (dino == nullptr || siglip == nullptr || frames_hwc == nullptr || workspace == nullptr) return BLB_ERR_ARG;
+  if (dino->patch_ldk != siglip->patch_ldk || patches_of(dino) != patches_of(siglip)) return BLB_ERR_SHAPE;
+  const size_t fused = align_up(blb_fused_workspace_bytes(dino, siglip, proj, batch));
+  const size_t pm = blb_patch_matrix_bytes(dino, batch);
+  if (fused == 0 || workspace_bytes < fused + pm) return BLB_ERR_WORKSPACE;
+  __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(workspace) + fused);
+  if (img_of(dino) != img_of(siglip)) return BLB_ERR_SHAPE;
+  BLB_TRY(u8_to_patches(frames_hwc, patches, batch, dino->patch_ldk, grid_of(dino), as_stream(stream), img_of(dino)));
+  return fused_forward(dino, siglip, proj, nullptr, nullptr, patches, batch, features, projected, workspace, fused, stream);
+}
+
+int blb_vit_tower_forward_u8(const blb_vit_weights* w, const uint8_t* frames_hwc, int batch, void* out, int ld_out,
+                             int out_col_off, void* workspace, size_t workspace_bytes, void* stream) {
+  if (w == nullptr || frames_hwc == nullptr || workspace == nullptr || batch <= 0) return BLB_ERR_ARG;
+  if (ld_out % 8 != 0 || out_col_off % 8 != 0) return BLB_ERR_ARG;
+  const size_t tower = align_up(tower_ws(w, batch).total);
+  const size_t pm = blb_patch_matrix_bytes(w, batch);
+  if (workspace_bytes < tower + pm) return BLB_ERR_WORKSPACE;
+  __nv_bfloat16* patches = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(workspace) + tower);
+  BLB_TRY(u8_to_patches(frames_hwc, patches, batch, w->patch_ldk, grid_of(w), as_stream(stream), img_of(w)));
+  return tower_forward(w, nullptr, batch, out, ld_out, out_col_off, workspace, tower, as_stream(stream), patches);
+}
+
+int blb_u8_to_patches(const uint8_t* frames_hwc, void* cols, int B, int ldk, int grid, int img_size, void* stream) {
+  return u8_to_patches(frames_hwc, bf(cols), B, ldk, grid, as_stream(stream), img_size);
+}
+
+int blb_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* dst, int Hd, int Wd, const int32_t* kx,
+                  const int32_t* bx, int ksx, const int32_t* ky, const int32_t* by, int ksy, uint8_t* tmp, void* stream) {
+  return resize_u8(src, B, Hs, Ws, dst, Hd, Wd, kx, bx, ksx, ky, by, ksy, tmp, as_stream(stream));
 }
 
 int blb_preprocess_u8(const uint8_t* frames_hwc, int batch, const void* lut_bf16, void* out_dino_bf16,

@@ -15,7 +15,8 @@ enum GemmEpilogueMode : int {
   EPI_BIAS = 0,       // out_bf16 = acc + bias
   EPI_BIAS_GELU = 1,  // out_bf16 = gelu_erf(acc + bias)
   EPI_RESIDUAL = 2,   // resid_f32 += gamma * (acc + bias); optional bf16 copy of the new residual (row-remapped)
-  EPI_PATCH = 3       // resid_f32[remap(row)] = acc + bias + pos[token]
+  EPI_PATCH = 3,      // resid_f32[remap(row)] = acc + bias + pos[token]
+  EPI_BIAS_QGELU = 4  // out_bf16 = quick_gelu(acc + bias) = x·σ(1.702 x)   (OpenAI CLIP towers, clip_vit.py:15-27)
 };
 
 struct GemmEpilogue {
@@ -110,6 +111,9 @@ void count_launch(int n);
 int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, __nv_bfloat16* y, int ldy, int rows,
                        int D, float eps, cudaStream_t stream, int reverse = 0);
 
+int layernorm_f32_f32(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int D,
+                      float eps, cudaStream_t stream);
+
 // fp32 rows → bf16 copy + full-row (sum, sumsq) in part 0 of `parts` (others zero): primes the LN-folded chain after
 // the patch-embed stage (the later blocks get both from the EPI_RESIDUAL epilogues)
 int rowstats_cast_f32_bf16(const float* x, int ldx, __nv_bfloat16* y, int ldy, float2* stats, int parts, int rows,
@@ -123,7 +127,12 @@ int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, i
 void attention_set_trace(long long* device_buffer);
 
 // patch_embed.cu — im2col for Conv2d(3, D, 14, stride 14) and the cls/reg prefix rows
-int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int ldk, cudaStream_t stream);
+int im2col_patch14(const __nv_bfloat16* pixels, __nv_bfloat16* cols, int B, int ldk, cudaStream_t stream, int grid = 16,
+                   int img = 0);
+int u8_to_patches(const uint8_t* frames, __nv_bfloat16* cols, int B, int ldk, int grid, cudaStream_t stream, int img = 0);
+// resize.cu — PIL-exact antialiased bicubic resize of uint8 HWC frames (two separable fixed-point passes)
+int resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* dst, int Hd, int Wd, const int* kx, const int* bx,
+              int ksx, const int* ky, const int* by, int ksy, uint8_t* tmp, cudaStream_t stream);
 int preprocess_u8(const uint8_t* frames, int B, const __nv_bfloat16* lut, __nv_bfloat16* out_dino,
                   __nv_bfloat16* out_siglip, cudaStream_t stream);
 int write_prefix_tokens(const float* prefix, float* resid, int B, int T, int n_prefix, int D, cudaStream_t stream);

@@ -38,7 +38,7 @@ constexpr int RCHUNK_BYTES = 32 * 32 * 4;   // one epilogue warp's [32 rows x 32
 constexpr int OCHUNK_BYTES = 32 * 32 * 2;   // one epilogue warp's [32 rows x 32 cols] bf16 output staging chunk
 constexpr int VEC_BYTES = 2 * 128 * 4;      // one epilogue warp's per-tile copy of two per-column fp32 vectors (<= 128 cols)
 
-template <int BN, int CTAS, int RTMA = 0, bool OBUF = false>
+template <int BN, int CTAS, int RTMA = 0, bool OBUF = false, bool FBUF = false>
 struct GemmCfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of W this CTA stages per k-block
   static constexpr int A_BYTES = BM * BK * 2;
@@ -51,7 +51,9 @@ struct GemmCfg {
   //       row-contiguous (coalesced) global stores
   // every epilogue warp also keeps this tile's slice of bias and of gamma / LN column sums in smem (VEC_BYTES): one
   // coalesced load per tile, issued before the accumulator is ready, instead of 8-16 dependent LDGs per 32-column chunk
-  static constexpr int STAGE_EPI_BYTES = RTMA ? NUM_EPI_WARPS * RTMA * RCHUNK_BYTES : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : 0);
+  // FBUF: one fp32 [32 x 32] staging chunk per epilogue warp (EPI_PATCH: transposed, coalesced fp32 row stores)
+  static constexpr int STAGE_EPI_BYTES = RTMA ? NUM_EPI_WARPS * RTMA * RCHUNK_BYTES
+                                              : (OBUF ? NUM_EPI_WARPS * OCHUNK_BYTES : (FBUF ? NUM_EPI_WARPS * RCHUNK_BYTES : 0));
   static constexpr int EPI_BYTES = STAGE_EPI_BYTES + NUM_EPI_WARPS * VEC_BYTES;
   // one CTA per SM: spend all 227 KB of shared memory on operand stages (the deeper ring lets the TMA producer run
   // further into the next tile while the current one drains)
@@ -80,8 +82,9 @@ template <int BN, int CTAS, int MODE, int RTMA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K, GemmEpilogue epi) {
-  constexpr bool OBUF = (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU);
-  using Cfg = GemmCfg<BN, CTAS, RTMA, OBUF>;
+  constexpr bool OBUF = (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU || MODE == EPI_BIAS_QGELU);
+  constexpr bool FBUF = (MODE == EPI_PATCH);
+  using Cfg = GemmCfg<BN, CTAS, RTMA, OBUF, FBUF>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(!RTMA || MODE == EPI_RESIDUAL, "TMA-staged residual only exists for EPI_RESIDUAL");
 
@@ -267,6 +270,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       const uint32_t obuf_s = smem_u32(smem_r) + ew * OCHUNK_BYTES;
+      // EPI_PATCH: in store pass k this lane writes 16 B of row (k*4 + lane/8) of the slab (fp32, 128 B per row)
+      long long p_dst[FBUF ? 8 : 1];
+      int p_tok[FBUF ? 8 : 1];
+      if constexpr (FBUF) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int gr = row0 + k * 4 + (lane >> 3);
+          int dr = gr, tk = 0;
+          const bool ok = map_row(epi, gr, dr, tk) && gr < M;
+          p_dst[k] = ok ? static_cast<long long>(dr) * epi.ld_resid : -1;
+          p_tok[k] = tk;
+        }
+      }
+      const uint32_t fbuf_s = smem_u32(smem_r) + ew * RCHUNK_BYTES;
 
       // folded LayerNorm, consumer side: rebuild (mean, rstd) of this lane's row from the producer's partial sums
       float ln_mean = 0.f, ln_rstd = 1.f;
@@ -366,10 +383,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           v[j] += __uint_as_float(b4.x); v[j + 1] += __uint_as_float(b4.y);
           v[j + 2] += __uint_as_float(b4.z); v[j + 3] += __uint_as_float(b4.w);
         }
-        if constexpr (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU) {
+        if constexpr (OBUF) {
           if constexpr (MODE == EPI_BIAS_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if constexpr (MODE == EPI_BIAS_QGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_quick(v[j]);
           }
           // stage this lane's row (64 B) in the warp's smem chunk: 16-byte piece j sits at j ^ ((row>>1)&3) so that
           // both this row-per-lane write and the transposed read below are bank-conflict free
@@ -395,17 +416,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (t_dst[k] >= 0) stg128(epi.out + t_dst[k] + col0 + (lane & 3) * 8, tv[k]);
           __syncwarp();
         } else if constexpr (MODE == EPI_PATCH) {
-          // out_f32[dst_row, col] = acc + bias + pos_embed[token, col]   (timm PatchEmbed + _pos_embed)
-          if (dst_ok) {
-            const float* p = epi.pos + static_cast<size_t>(tok) * N + col0;
-            float* x = epi.resid + static_cast<size_t>(dst_row) * epi.ld_resid + col0;
+          // out_f32[dst_row, col] = acc + bias + pos_embed[token, col]   (timm PatchEmbed + _pos_embed): the lane's row
+          // (acc + bias) goes through the warp's swizzled smem chunk so that both the pos_embed read and the fp32 store
+          // are row-contiguous (4 rows x 128 B per instruction instead of 32 rows x 16 B)
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 p4 = __ldg(reinterpret_cast<const float4*>(p + j));
-              float4 o4 = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
-              *reinterpret_cast<float4*>(x + j) = o4;
+          for (int j = 0; j < 8; ++j)
+            sts128(fbuf_s + lane * 128 + ((j ^ (lane & 7)) << 4),
+                   make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                              __float_as_uint(v[4 * j + 3])));
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = k * 4 + (lane >> 3), j = lane & 7;
+            const uint4 t4 = lds128(fbuf_s + r * 128 + ((j ^ (r & 7)) << 4));
+            if (p_dst[k] >= 0) {
+              float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (epi.pos != nullptr)
+                p4 = __ldg(reinterpret_cast<const float4*>(epi.pos + static_cast<size_t>(p_tok[k]) * N + col0 + j * 4));
+              const uint4 o4 = make_uint4(__float_as_uint(__uint_as_float(t4.x) + p4.x), __float_as_uint(__uint_as_float(t4.y) + p4.y),
+                                          __float_as_uint(__uint_as_float(t4.z) + p4.z), __float_as_uint(__uint_as_float(t4.w) + p4.w));
+              stg128(epi.resid + p_dst[k] + col0 + j * 4, o4);
             }
           }
+          __syncwarp();
         } else {  // EPI_RESIDUAL:  x += gamma * (acc + bias)   (timm Block: x + ls(branch(x)))
           if (row_ok) {
             float* x = epi.resid + static_cast<size_t>(row) * epi.ld_resid + col0;
@@ -667,7 +700,8 @@ int num_sms() {   // of the CURRENT device (cached per device)
 template <int BN, int CTAS, int MODE, int RTMA>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, int M, int N, int K,
                   const GemmEpilogue& epi, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTAS, RTMA, (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU)>;
+  using Cfg = GemmCfg<BN, CTAS, RTMA, (MODE == EPI_BIAS || MODE == EPI_BIAS_GELU || MODE == EPI_BIAS_QGELU),
+                      (MODE == EPI_PATCH)>;
   auto kern = gemm_bf16_kernel<BN, CTAS, MODE, RTMA>;
   static std::atomic<bool> configured[BLB_MAX_DEVICES];   // the attribute is per device; setting it twice is harmless
   if (!configured[current_device()].load(std::memory_order_acquire)) {
@@ -709,6 +743,7 @@ static int launch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, i
   switch (mode) {
     case EPI_BIAS: return launch<BN, CTAS, EPI_BIAS, 0>(ta, tb, ta, M, N, K, epi, s);
     case EPI_BIAS_GELU: return launch<BN, CTAS, EPI_BIAS_GELU, 0>(ta, tb, ta, M, N, K, epi, s);
+    case EPI_BIAS_QGELU: return launch<BN, CTAS, EPI_BIAS_QGELU, 0>(ta, tb, ta, M, N, K, epi, s);
     case EPI_PATCH: return launch<BN, CTAS, EPI_PATCH, 0>(ta, tb, ta, M, N, K, epi, s);
     case EPI_RESIDUAL: {
       if (g_resid_direct) return launch<BN, CTAS, EPI_RESIDUAL, 0>(ta, tb, ta, M, N, K, epi, s);
@@ -730,7 +765,8 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int ldw, 
   if (M <= 0 || N <= 0 || K <= 0 || A == nullptr || W == nullptr) return BLB_ERR_ARG;
   const int bn = pick_bn(N);
   if (bn == 0) return BLB_ERR_SHAPE;
-  if (epi.ln_stats != nullptr && (epi.ln_colsum == nullptr || epi.ln_parts <= 0 || mode > EPI_BIAS_GELU)) return BLB_ERR_ARG;
+  const bool bf16_out_mode = mode == EPI_BIAS || mode == EPI_BIAS_GELU || mode == EPI_BIAS_QGELU;
+  if (epi.ln_stats != nullptr && (epi.ln_colsum == nullptr || epi.ln_parts <= 0 || !bf16_out_mode)) return BLB_ERR_ARG;
   if ((epi.stats_out != nullptr || epi.xb_out != nullptr) && mode != EPI_RESIDUAL) return BLB_ERR_ARG;
   if (epi.shift_out != nullptr && (epi.ln_stats == nullptr || epi.shift_in == epi.shift_out)) return BLB_ERR_ARG;   // ping-pong
   if (epi.shift_in != nullptr && mode == EPI_PATCH) return BLB_ERR_ARG;

@@ -9,11 +9,12 @@
 
 namespace blb {
 
-template <int VEC>  // D = VEC * 128
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
+// F32OUT: fp32 output (may alias the input: the row lives in registers) — timm `norm_pre` of the CLIP towers, which
+// rewrites the residual stream itself before block 0
+template <int VEC, bool F32OUT = false>  // D = VEC * 128
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
                                                         const float* __restrict__ w, const float* __restrict__ b,
-                                                        __nv_bfloat16* __restrict__ y, int ldy, int rows, float eps,
-                                                        int reverse) {
+                                                        void* y, int ldy, int rows, float eps, int reverse) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk = reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
   const int row = blk * 8 + warp;
@@ -42,15 +43,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = rsqrtf(q * (1.0f / D) + eps);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   const float4* b4 = reinterpret_cast<const float4*>(b);
-  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
+  uint2* yr = reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + static_cast<size_t>(row) * ldy);
+  float4* yf = reinterpret_cast<float4*>(static_cast<float*>(y) + static_cast<size_t>(row) * ldy);
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const float4 ww = __ldg(w4 + lane + 32 * j);
     const float4 bb = __ldg(b4 + lane + 32 * j);
-    uint2 o;
-    o.x = pack_bf16x2((v[j].x - mean) * rstd * ww.x + bb.x, (v[j].y - mean) * rstd * ww.y + bb.y);
-    o.y = pack_bf16x2((v[j].z - mean) * rstd * ww.z + bb.z, (v[j].w - mean) * rstd * ww.w + bb.w);
-    yr[lane + 32 * j] = o;
+    const float o0 = (v[j].x - mean) * rstd * ww.x + bb.x, o1 = (v[j].y - mean) * rstd * ww.y + bb.y;
+    const float o2 = (v[j].z - mean) * rstd * ww.z + bb.z, o3 = (v[j].w - mean) * rstd * ww.w + bb.w;
+    if constexpr (F32OUT) {
+      yf[lane + 32 * j] = make_float4(o0, o1, o2, o3);
+    } else {
+      uint2 o;
+      o.x = pack_bf16x2(o0, o1);
+      o.y = pack_bf16x2(o2, o3);
+      yr[lane + 32 * j] = o;
+    }
   }
 }
 
@@ -63,11 +71,31 @@ int layernorm_f32_bf16(const float* x, int ldx, const float* w, const float* b, 
   TimingScope ts(TIME_LAYERNORM, 6.0 * rows * D, stream);   // bytes: fp32 read + bf16 write
   switch (D / 128) {
 #define BLB_LN_CASE(V) \
-  case V: le = launch_pdl(layernorm_kernel<V>, grid, block, 0, stream, x, ldx, w, b, y, ldy, rows, eps, reverse); break;
+  case V: le = launch_pdl(layernorm_kernel<V, false>, grid, block, 0, stream, x, ldx, w, b, static_cast<void*>(y), ldy, rows, eps, reverse); break;
     BLB_LN_CASE(1) BLB_LN_CASE(2) BLB_LN_CASE(3) BLB_LN_CASE(4) BLB_LN_CASE(5) BLB_LN_CASE(6) BLB_LN_CASE(7)
     BLB_LN_CASE(8) BLB_LN_CASE(9) BLB_LN_CASE(10) BLB_LN_CASE(11) BLB_LN_CASE(12) BLB_LN_CASE(13)
     BLB_LN_CASE(14) BLB_LN_CASE(15) BLB_LN_CASE(16)
 #undef BLB_LN_CASE
+    default: return BLB_ERR_SHAPE;
+  }
+  count_launch(1);
+  if (le != cudaSuccess) return static_cast<int>(le);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// timm norm_pre (pre_norm=True, the CLIP towers): fp32 rows → fp32 rows, in place allowed
+int layernorm_f32_f32(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int rows, int D,
+                      float eps, cudaStream_t stream) {
+  if (x == nullptr || w == nullptr || b == nullptr || y == nullptr || rows <= 0) return BLB_ERR_ARG;
+  if (D % 128 != 0 || D > 2048 || ldx % 4 != 0 || ldy % 4 != 0) return BLB_ERR_SHAPE;
+  const dim3 grid((rows + 7) / 8), block(256);
+  cudaError_t le = cudaSuccess;
+  TimingScope ts(TIME_LAYERNORM, 8.0 * rows * D, stream);
+  switch (D / 128) {
+#define BLB_LNF_CASE(V) \
+  case V: le = launch_pdl(layernorm_kernel<V, true>, grid, block, 0, stream, x, ldx, w, b, static_cast<void*>(y), ldy, rows, eps, 0); break;
+    BLB_LNF_CASE(6) BLB_LNF_CASE(8) BLB_LNF_CASE(9) BLB_LNF_CASE(10) BLB_LNF_CASE(12)
+#undef BLB_LNF_CASE
     default: return BLB_ERR_SHAPE;
   }
   count_launch(1);

@@ -318,6 +318,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(p, t, -1.000060678e+00f);
   return fmaf(-a, ex2_approx(p), fmaxf(x, 0.f));
 }
+// quick-GELU of the OpenAI CLIP checkpoints (timm `quick_gelu`: x * sigmoid(1.702 x)) = x / (1 + 2^(-1.702·log2e·x))
+__device__ __forceinline__ float gelu_quick(float x) {
+  const float e = ex2_approx(-2.4554669595930157f * x);   // 1.702 * log2(e)
+  return __fdividef(x, 1.0f + e);
+}
 // reference formulation (CUDA erff, <= 1 ulp) kept for A/B checks in tests/tools
 __device__ __forceinline__ float gelu_erf_libm(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

@@ -272,6 +272,52 @@ def preprocess_u8(frames: torch.Tensor, lut: torch.Tensor):
     return dino, siglip
 
 
+_RESIZE_TABLES: dict = {}
+
+
+def _resize_tables(in_size: int, out_size: int, interpolation: str, device: torch.device):
+    from .resize import resample_coeffs
+    key = (in_size, out_size, interpolation, device)
+    t = _RESIZE_TABLES.get(key)
+    if t is None:
+        kk, bounds, ksize = resample_coeffs(in_size, out_size, interpolation)
+        t = (torch.from_numpy(kk).to(device), torch.from_numpy(bounds).to(device), ksize)
+        _RESIZE_TABLES[key] = t
+    return t
+
+
+def resize_u8(frames: torch.Tensor, out_hw, interpolation: str = "bicubic") -> torch.Tensor:
+    """uint8 HWC frames [B,H,W,3] on the GPU → [B,Hd,Wd,3], bit-exact with PIL.Image.resize((Wd,Hd), BICUBIC) — the
+    antialiased Resize of the reference's image transform (Pillow's fixed-point two-pass resampler on the device)."""
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_contiguous()
+    B, Hs, Ws, _ = frames.shape
+    Hd, Wd = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((B, Hd, Wd, 3), dtype=torch.uint8, device=frames.device)
+    if B == 0:
+        return out
+    kx, bx, ksx = _resize_tables(Ws, Wd, interpolation, frames.device) if Wd != Ws else (None, None, 0)
+    ky, by, ksy = _resize_tables(Hs, Hd, interpolation, frames.device) if Hd != Hs else (None, None, 0)
+    tmp = torch.empty((B, Hs, Wd, 3), dtype=torch.uint8, device=frames.device) if (Wd != Ws and Hd != Hs) else None
+    with on_device(frames):
+        _lib.check(_lib.load().blb_resize_u8(frames.data_ptr(), B, Hs, Ws, out.data_ptr(), Hd, Wd, _ptr(kx), _ptr(bx), ksx,
+                                             _ptr(ky), _ptr(by), ksy, _ptr(tmp), _stream()), "resize_u8")
+    return out
+
+
+def u8_to_patches(frames: torch.Tensor, ldk: int = 592) -> torch.Tensor:
+    """uint8 HWC frames [B,S,S,3] (S a multiple of 14) → bf16 [B*(S/14)², ldk], k = kh*42 + kw*3 + c, exact 0..255."""
+    _need_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_contiguous()
+    B, S = frames.shape[0], frames.shape[1]
+    grid = S // 14
+    cols = torch.empty((B * grid * grid, ldk), dtype=torch.bfloat16, device=frames.device)
+    with on_device(frames):
+        _lib.check(_lib.load().blb_u8_to_patches(frames.data_ptr(), cols.data_ptr(), B, ldk, grid, S, _stream()),
+                   "u8_to_patches")
+    return cols
+
+
 def encode_actions(actions: torch.Tensor, bins: torch.Tensor, min_action: float, max_action: float,
                    vocab_size: int) -> torch.Tensor:
     """clip → np.digitize(bins) → vocab_size − index, on the device; actions float32/float64, any shape."""

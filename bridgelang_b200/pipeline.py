@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib, ops
 from .config import NUM_PATCHES
 from .projector import FusedMLPProjector, PrismaticProjector
-from .vision import DinoSigLIPViTBackbone, PrismaticVisionBackbone, _as_pixels
+from .vision import DinoSigLIPViTBackbone, PrismaticVisionBackbone, _as_pixels, _FusedBackbone
 
 
 class VisualPrefixEncoder(nn.Module):
@@ -32,8 +32,9 @@ class VisualPrefixEncoder(nn.Module):
         super().__init__()
         self.vision_backbone = vision_backbone
         self.projector = projector
-        if isinstance(vision_backbone, DinoSigLIPViTBackbone):
-            self._towers = (vision_backbone.dino_featurizer, vision_backbone.siglip_featurizer)
+        if isinstance(vision_backbone, _FusedBackbone):          # DinoSigLIP (224 / 384 px) and DinoCLIP (336 px)
+            self._towers = vision_backbone._towers()
+            self._keys = vision_backbone.KEYS
         elif isinstance(vision_backbone, PrismaticVisionBackbone) and vision_backbone.use_fused_vision_backbone:
             self._towers = (vision_backbone.featurizer, vision_backbone.fused_featurizer)
         else:
@@ -41,24 +42,25 @@ class VisualPrefixEncoder(nn.Module):
         if not isinstance(projector, (FusedMLPProjector, PrismaticProjector)):
             raise ValueError("VisualPrefixEncoder needs a FusedMLPProjector / PrismaticProjector")
 
-    @staticmethod
-    def _split(pixel_values) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _split(self, pixel_values) -> Tuple[torch.Tensor, torch.Tensor]:
         if isinstance(pixel_values, dict):
-            return pixel_values["dino"], pixel_values["siglip"]
+            k0, k1 = getattr(self, "_keys", ("dino", "siglip"))
+            return pixel_values[k0], pixel_values[k1]
         img, img_fused = torch.split(pixel_values, [3, 3], dim=1)   # modeling_prismatic.py:120
         return img, img_fused
 
     @torch.no_grad()
     def forward(self, pixel_values, return_features: bool = False):
         dino_px, siglip_px = self._split(pixel_values)
-        dino_px, siglip_px = _as_pixels(dino_px), _as_pixels(siglip_px)
+        cfg0, cfg1 = self._towers[0].cfg, self._towers[1].cfg
+        dino_px, siglip_px = _as_pixels(dino_px, cfg0.img_size), _as_pixels(siglip_px, cfg1.img_size)
         B, dev = dino_px.shape[0], dino_px.device
         lib = _lib.load()
         dino, siglip = self._towers[0].packed(), self._towers[1].packed()
         proj = self.projector.packed()
         fused_dim = dino.struct.dim + siglip.struct.dim
-        feats = torch.empty((B, NUM_PATCHES, fused_dim), dtype=torch.bfloat16, device=dev)
-        out = torch.empty((B, NUM_PATCHES, proj.out_dim), dtype=torch.bfloat16, device=dev)
+        feats = torch.empty((B, cfg0.num_patches, fused_dim), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((B, cfg0.num_patches, proj.out_dim), dtype=torch.bfloat16, device=dev)
         if B == 0:
             return (out, feats) if return_features else out
         need = lib.blb_fused_workspace_bytes(C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), B)
@@ -71,13 +73,40 @@ class VisualPrefixEncoder(nn.Module):
         return (out, feats) if return_features else out
 
     @torch.no_grad()
-    def forward_uint8(self, frames: torch.Tensor, return_features: bool = False):
-        """Already-resized uint8 frames [B,224,224,3] on the GPU → projected prefix (device-side ToTensor + both
-        Normalizes), then exactly `forward`."""
-        if not isinstance(self.vision_backbone, DinoSigLIPViTBackbone):
-            raise ValueError("forward_uint8 needs the native DinoSigLIPViTBackbone (dict pixel_values)")
-        return self.forward(self.vision_backbone.preprocess_uint8(frames), return_features=return_features)
+    def forward_uint8(self, frames: torch.Tensor, return_features: bool = False, folded: bool = True):
+        """Already-resized uint8 frames [B,224,224,3] on the GPU → projected prefix.
 
+        folded=True (default): ToTensor and each tower's Normalize live inside that tower's patch-embed weights, and —
+        stride == kernel making im2col a pure permutation — the frame is written ONCE in patch-major order as exact bf16
+        integers: that matrix is the TMA-loaded A operand of BOTH towers' patch-embed GEMMs (one C-ABI call,
+        `blb_fused_featurize_project_forward_u8`).  No normalized frames, no per-tower im2col pass.
+        folded=False: the round-1 route — a LUT kernel writes both normalized bf16 frames (bit-identical to the host
+        transform), then exactly `forward`."""
+        if not folded:
+            if not isinstance(self.vision_backbone, DinoSigLIPViTBackbone):
+                raise ValueError("forward_uint8(folded=False) needs the native DinoSigLIPViTBackbone (dict pixel_values)")
+            return self.forward(self.vision_backbone.preprocess_uint8(frames), return_features=return_features)
+        from .vision import _as_frames
+        cfg = self._towers[0].cfg
+        fr = _as_frames(frames, cfg.img_size)
+        B, dev = fr.shape[0], fr.device
+        lib = _lib.load()
+        dino, siglip = self._towers[0].packed(), self._towers[1].packed()
+        proj = self.projector.packed()
+        fused_dim = dino.struct.dim + siglip.struct.dim
+        feats = torch.empty((B, cfg.num_patches, fused_dim), dtype=torch.bfloat16, device=dev)
+        out = torch.empty((B, cfg.num_patches, proj.out_dim), dtype=torch.bfloat16, device=dev)
+        if B == 0:
+            return (out, feats) if return_features else out
+        fused = lib.blb_fused_workspace_bytes(C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), B)
+        need = (fused + 255) // 256 * 256 + lib.blb_patch_matrix_bytes(C.byref(dino.struct), B)
+        with ops.on_device(fr, self._towers[0].pos_embed, self._towers[1].pos_embed, feats, out):
+            ws = ops.shared_workspace(dev, need)
+            _lib.check(lib.blb_fused_featurize_project_forward_u8(
+                C.byref(dino.struct), C.byref(siglip.struct), C.byref(proj), fr.data_ptr(), B, feats.data_ptr(),
+                out.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+                "fused_featurize_project_forward_u8")
+        return (out, feats) if return_features else out
 
     def stream(self, host_batches, uint8: bool = False, to_host: bool = False):
         """Serving loop with double-buffered input staging: yields the projected prefix of every batch in

@@ -25,15 +25,22 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .config import (DINOV2_L14_REG4, LN_EPS, NUM_PATCHES, PATCH, PATCH_K, PATCH_LDK, SIGLIP_SO400M_14, VitConfig)
+from .config import (CLIP_L14_336, DINOV2_L14_REG4, DINOV2_L14_REG4_336, DINOV2_L14_REG4_384, LN_EPS, NUM_PATCHES, PATCH,
+                     PATCH_K, PATCH_LDK, SIGLIP_SO400M_14, SIGLIP_SO400M_14_384, VitConfig)
 from .weights import DINO_MEAN, DINO_STD, SIGLIP_MEAN, SIGLIP_STD
 
-# Registry =>> same ids as dinosiglip_vit.py:21-30 / siglip_vit.py:8-13 / dinov2_vit.py:9-10 (224 px members)
+# Registry =>> same ids as dinosiglip_vit.py:21-30 / dinoclip_vit.py:22-27 / siglip_vit.py:8-13 / dinov2_vit.py:9-10 /
+# clip_vit.py:8-12, keyed additionally by the `default_image_size` materialize.py:35-49 passes
 DINOSigLIP_VISION_BACKBONES = {
     "dinosiglip-vit-so-224px": {"dino": DINOV2_L14_REG4, "siglip": SIGLIP_SO400M_14},
+    "dinosiglip-vit-so-384px": {"dino": DINOV2_L14_REG4_384, "siglip": SIGLIP_SO400M_14_384},
 }
-SIGLIP_VISION_BACKBONES = {"siglip-vit-so400m": SIGLIP_SO400M_14}
+DINOCLIP_VISION_BACKBONES = {
+    "dinoclip-vit-l-336px": {"dino": DINOV2_L14_REG4_336, "clip": CLIP_L14_336},
+}
+SIGLIP_VISION_BACKBONES = {"siglip-vit-so400m": SIGLIP_SO400M_14, "siglip-vit-so400m-384px": SIGLIP_SO400M_14_384}
 DINOv2_VISION_BACKBONES = {"dinov2-vit-l": DINOV2_L14_REG4}
+CLIP_VISION_BACKBONES = {"clip-vit-l-336px": CLIP_L14_336}
 TIMM_ID_TO_CONFIG = {c.timm_id: c for c in (DINOV2_L14_REG4, SIGLIP_SO400M_14)}
 
 
@@ -96,9 +103,9 @@ class Block(nn.Module):
 
 
 class _PatchEmbed(nn.Module):
-    def __init__(self, dim: int) -> None:
+    def __init__(self, dim: int, bias: bool = True) -> None:
         super().__init__()
-        self.proj = nn.Conv2d(3, dim, kernel_size=PATCH, stride=PATCH, bias=True)
+        self.proj = nn.Conv2d(3, dim, kernel_size=PATCH, stride=PATCH, bias=bias)
 
 
 class _AttentionPool(nn.Module):
@@ -125,12 +132,15 @@ class VisionTransformer(nn.Module):
         self.cfg = cfg
         self.embed_dim = cfg.dim
         D = cfg.dim
-        self.patch_embed = _PatchEmbed(D)
+        self.patch_embed = _PatchEmbed(D, bias=cfg.patch_bias)     # timm: bias = not pre_norm
         if cfg.class_token:
             self.cls_token = nn.Parameter(torch.zeros(1, 1, D))
         if cfg.reg_tokens:
             self.reg_token = nn.Parameter(torch.zeros(1, cfg.reg_tokens, D))
-        self.pos_embed = nn.Parameter(torch.zeros(1, NUM_PATCHES, D))
+        # timm: num_patches rows when no_embed_class, else num_patches + num_prefix_tokens (the CLIP checkpoints)
+        self.pos_embed = nn.Parameter(torch.zeros(1, cfg.num_patches + (0 if cfg.no_embed_class else cfg.n_prefix), D))
+        if cfg.pre_norm:
+            self.norm_pre = nn.LayerNorm(D, eps=LN_EPS)
         self.blocks = nn.ModuleList([Block(cfg, ls_param_name) for _ in range(cfg.depth)])
         self.norm = nn.LayerNorm(D, eps=LN_EPS)
         if cfg.attn_pool:
@@ -167,7 +177,7 @@ class VisionTransformer(nn.Module):
         lib = _lib.load()
         pk = self.packed()
         B = pixels.shape[0]
-        px = _as_pixels(pixels)
+        px = _as_pixels(pixels, self.cfg.img_size)
         if B == 0:                      # an empty shard (more ranks than images): nothing to launch
             return
         need = lib.blb_vit_workspace_bytes(C.byref(pk.struct), B)
@@ -179,8 +189,32 @@ class VisionTransformer(nn.Module):
 
     def forward(self, pixels: torch.Tensor) -> torch.Tensor:
         B = pixels.shape[0]
-        out = torch.empty((B, NUM_PATCHES, self.cfg.dim), dtype=torch.bfloat16, device=pixels.device)
+        out = torch.empty((B, self.cfg.num_patches, self.cfg.dim), dtype=torch.bfloat16, device=pixels.device)
         self.forward_into(pixels, out, 0)
+        return out
+
+    @torch.no_grad()
+    def forward_uint8_into(self, frames: torch.Tensor, out: torch.Tensor, col_off: int) -> None:
+        """uint8 HWC frames [B, img, img, 3] (already resized; on the GPU) → this tower's column slice of `out`.
+        ToTensor + this tower's Normalize are folded into the patch-embed weights: the frame goes
+        through one permutation kernel into the TMA-loaded A operand of the patch-embed GEMM."""
+        lib = _lib.load()
+        pk = self.packed()
+        fr = _as_frames(frames, self.cfg.img_size)
+        B = fr.shape[0]
+        if B == 0:
+            return
+        need = lib.blb_vit_workspace_bytes(C.byref(pk.struct), B)
+        with ops.on_device(fr, out, self.pos_embed):
+            ws = self.workspace(need)
+            _lib.check(lib.blb_vit_tower_forward_u8(C.byref(pk.struct), fr.data_ptr(), B, out.data_ptr(), out.stride(-2),
+                                                    col_off, ws.data_ptr(), ws.numel(),
+                                                    torch.cuda.current_stream().cuda_stream), "vit_tower_forward_u8")
+
+    def forward_uint8(self, frames: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((frames.shape[0], self.cfg.num_patches, self.cfg.dim), dtype=torch.bfloat16,
+                          device=frames.device)
+        self.forward_uint8_into(frames, out, 0)
         return out
 
     def get_intermediate_layers(self, x: torch.Tensor, n=None, **_: Any) -> Tuple[torch.Tensor]:
@@ -191,12 +225,20 @@ class VisionTransformer(nn.Module):
         return (self.forward(x),)
 
 
-def _as_pixels(pixels: torch.Tensor) -> torch.Tensor:
+def _as_pixels(pixels: torch.Tensor, img: int = 224) -> torch.Tensor:
     if not pixels.is_cuda:
         raise RuntimeError("pixel_values must be CUDA tensors (no CPU fallback)")
-    if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, 224, 224):
-        raise ValueError(f"expected pixel_values [B,3,224,224], got {tuple(pixels.shape)}")
+    if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, img, img):
+        raise ValueError(f"expected pixel_values [B,3,{img},{img}], got {tuple(pixels.shape)}")
     return pixels.to(torch.bfloat16).contiguous()
+
+
+def _as_frames(frames: torch.Tensor, img: int = 224) -> torch.Tensor:
+    if not frames.is_cuda:
+        raise RuntimeError("uint8 frames must be CUDA tensors (no CPU fallback)")
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or tuple(frames.shape[1:]) != (img, img, 3):
+        raise ValueError(f"expected uint8 frames [B,{img},{img},3] (HWC), got {frames.dtype} {tuple(frames.shape)}")
+    return frames.contiguous()
 
 
 class _PackedTower:
@@ -221,14 +263,34 @@ class _PackedTower:
             self.keep.append(t)
             return t
 
+        conv_w = vit.patch_embed.proj.weight.detach().to(dev).float()                          # [D, 3, 14, 14]
+        conv_b = (vit.patch_embed.proj.bias.detach().to(dev).float() if cfg.patch_bias
+                  else torch.zeros(D, dtype=torch.float32, device=dev))
         pw = torch.zeros((D, PATCH_LDK), dtype=torch.float32, device=dev)
-        pw[:, :PATCH_K] = vit.patch_embed.proj.weight.detach().reshape(D, PATCH_K).float()   # (c, kh, kw) order
+        pw[:, :PATCH_K] = conv_w.reshape(D, PATCH_K)                                           # (c, kh, kw) order
+        # uint8 entry: ToTensor + Normalize folded in — conv((u/255 − mean_c)/std_c) =
+        # Σ W/(255·std_c)·u + (b − Σ W·mean_c/std_c) — and K reordered to (kh, kw, c), the order of an HWC patch row
+        mean = torch.tensor(cfg.mean, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+        std = torch.tensor(cfg.std, dtype=torch.float32, device=dev).view(1, 3, 1, 1)
+        pw8 = torch.zeros((D, PATCH_LDK), dtype=torch.float32, device=dev)
+        pw8[:, :PATCH_K] = (conv_w / (255.0 * std)).permute(0, 2, 3, 1).reshape(D, PATCH_K)
+        pb8 = conv_b - (conv_w * (mean / std)).sum(dim=(1, 2, 3))
+        # prefix rows (cls, reg): input independent.  With no_embed_class=False (CLIP) pos_embed also has rows for them:
+        # fold those into the prefix rows and hand the kernels the patch rows only
+        pos = vit.pos_embed.detach().to(dev).float().reshape(-1, D)
+        pos_prefix = None
+        if not cfg.no_embed_class and cfg.n_prefix:
+            pos_prefix, pos = pos[:cfg.n_prefix], pos[cfg.n_prefix:]
         prefix = []
         if cfg.class_token:
-            prefix.append(vit.cls_token.detach().reshape(1, D))
+            prefix.append(vit.cls_token.detach().to(dev).float().reshape(1, D))
         if cfg.reg_tokens:
-            prefix.append(vit.reg_token.detach().reshape(cfg.reg_tokens, D))
-        self.prefix = f32(torch.cat(prefix, dim=0)) if prefix else None
+            prefix.append(vit.reg_token.detach().to(dev).float().reshape(cfg.reg_tokens, D))
+        if prefix:
+            rows = torch.cat(prefix, dim=0)
+            self.prefix = f32(rows + pos_prefix if pos_prefix is not None else rows)
+        else:
+            self.prefix = None
 
         # norm1 → attn.qkv and norm2 → mlp.fc1 folded (default): LN(x)·Wᵀ + b = rstd·(x·W'ᵀ − mean·colsum(W')) + b'
         # with W' = W·diag(ln_w) rounded to bf16 once, colsum over the ROUNDED W' (so the mean term cancels exactly
@@ -274,9 +336,14 @@ class _PackedTower:
         s.dim, s.heads, s.head_dim, s.hidden_pad = D, cfg.heads, cfg.head_dim, Hp
         s.n_prefix, s.n_blocks, s.patch_ldk, s.ln_eps = cfg.n_prefix, n_blocks, PATCH_LDK, LN_EPS
         s.patch_w = b16(pw).data_ptr()
-        s.patch_b = f32(vit.patch_embed.proj.bias).data_ptr()
-        s.pos_embed = f32(vit.pos_embed.reshape(NUM_PATCHES, D)).data_ptr()
+        s.patch_b = f32(conv_b).data_ptr() if cfg.patch_bias else None
+        s.pos_embed = f32(pos.reshape(cfg.num_patches, D)).data_ptr()
         s.prefix = self.prefix.data_ptr() if self.prefix is not None else None
+        s.grid, s.img_size = cfg.grid, cfg.img_size
+        s.act = {"gelu": 0, "quick_gelu": 1}[cfg.act]
+        if cfg.pre_norm:
+            s.norm_pre_w, s.norm_pre_b = f32(vit.norm_pre.weight).data_ptr(), f32(vit.norm_pre.bias).data_ptr()
+        s.patch_w_u8, s.patch_b_u8 = b16(pw8).data_ptr(), f32(pb8).data_ptr()
         s.blocks_host = C.cast(self.blocks, C.POINTER(_lib.BlockWeights))
         s.ln_folded = 1 if self.ln_folded else 0
         s.hidden = Hm
@@ -423,25 +490,52 @@ class PrismaticImageProcessor:
     def __call__(self, images, **kwargs):
         return self.preprocess(images, **kwargs)
 
-    def preprocess_to_device(self, images, device="cuda") -> torch.Tensor:
-        """[B, 6, 224, 224] bf16 on the device, bit-identical to `preprocess(...)["pixel_values"].to(device, bf16)` for the
-        fused 224 px DINOv2 + SigLIP configuration (both towers resize identically, so one uint8 frame feeds both)."""
-        import numpy as np
+    def _check_fused_224(self) -> None:
         if not (self.use_fused_vision_backbone and len(self.input_sizes) == 2
                 and all(tuple(sz) == (3, 224, 224) for sz in self.input_sizes)
                 and self.tvf_resize_params[0] == self.tvf_resize_params[1]
                 and [tuple(m) for m in self.means] == [tuple(DINO_MEAN), tuple(SIGLIP_MEAN)]
                 and [tuple(sd) for sd in self.stds] == [tuple(DINO_STD), tuple(SIGLIP_STD)]):
-            raise ValueError("preprocess_to_device covers the fused 224 px DINOv2 + SigLIP processor configuration")
+            raise ValueError("the device preprocessing path covers the fused 224 px DINOv2 + SigLIP processor configuration")
+
+    def frames_to_device(self, images, device="cuda", device_resize: bool = True) -> torch.Tensor:
+        """PIL images → uint8 HWC frames [B,224,224,3] on the device, byte-identical to what the host transform feeds
+        ToTensor (letterbox → bicubic Resize → CenterCrop).  device_resize=True: only the RAW frame crosses PCIe and the
+        antialiased bicubic resize runs on the GPU (`ops.resize_u8`, bit-exact with PIL); images of different sizes
+        are resized one by one.  The result feeds `VisualPrefixEncoder.forward_uint8`."""
+        import numpy as np
+        self._check_fused_224()
         if not isinstance(images, list):
             images = [images]
-        frames = []
+        out = []
         for img in images:
             img = img.convert("RGB")
             if self.tvf_do_letterbox:
                 img = letterbox_pad_transform(img, self.tvf_letterbox_fill)
-            frames.append(np.asarray(self._resized(img, 0), dtype=np.uint8))
-        u8 = torch.from_numpy(np.stack(frames)).pin_memory().to(device, non_blocking=True)
+            if not device_resize:
+                out.append(torch.from_numpy(np.array(self._resized(img, 0), dtype=np.uint8)).to(device))
+                continue
+            raw = torch.from_numpy(np.array(img, dtype=np.uint8)).to(device, non_blocking=True)[None].contiguous()
+            size = self.tvf_resize_params[0]["size"]
+            H, W = raw.shape[1], raw.shape[2]
+            if isinstance(size, (tuple, list)):                    # resize-naive: exact (h, w)
+                Hd, Wd = int(size[0]), int(size[1])
+            else:                                                  # torchvision: shorter side → size, aspect kept
+                short, long = (W, H) if W <= H else (H, W)
+                new_short, new_long = int(size), int(size * long / short)
+                Wd, Hd = (new_short, new_long) if W <= H else (new_long, new_short)
+            fr = ops.resize_u8(raw, (Hd, Wd))[0]
+            ch, cw = self.tvf_crop_params[0]["output_size"]
+            top, left = int(round((Hd - ch) / 2.0)), int(round((Wd - cw) / 2.0))   # torchvision center_crop
+            out.append(fr[top:top + ch, left:left + cw].contiguous())
+        return torch.stack(out)
+
+    def preprocess_to_device(self, images, device="cuda", device_resize: bool = False) -> torch.Tensor:
+        """[B, 6, 224, 224] bf16 on the device, bit-identical to `preprocess(...)["pixel_values"].to(device, bf16)` for the
+        fused 224 px DINOv2 + SigLIP configuration (both towers resize identically, so one uint8 frame feeds both):
+        ToTensor + both Normalizes + the bf16 cast are one LUT kernel; with device_resize=True the bicubic resize runs
+        on the GPU as well (PIL-exact), so the host only decodes the image."""
+        u8 = self.frames_to_device(images, device=device, device_resize=device_resize)
         if self._lut is None or self._lut.device != u8.device:
             self._lut = make_preprocess_lut(u8.device)
         dino, siglip = ops.preprocess_u8(u8, self._lut)
@@ -495,66 +589,118 @@ def _vit_fsdp_policy() -> Callable:
     return partial(_or_policy, policies=[vit_wrap_policy, transformer_block_policy])
 
 
-class DinoSigLIPViTBackbone(VisionBackbone):
-    """dinosiglip_vit.py:43-163.  `forward({"dino": [B,3,224,224], "siglip": [B,3,224,224]}) -> [B,256,2176]`
-    (cols 0-1023 DINOv2, 1024-2175 SigLIP).  Each tower's last needed fc2 epilogue writes its column slice of the
-    output directly, so the reference's torch.cat copy does not exist."""
+class _FusedBackbone(VisionBackbone):
+    """Two towers on the same frame, patch tokens concatenated channel-wise (dinosiglip_vit.py:142-147,
+    dinoclip_vit.py:141-147).  Each tower's last needed fc2 epilogue writes its column slice of the output directly, so
+    the reference's torch.cat copy does not exist."""
 
-    def __init__(self, vision_backbone_id: str, image_resize_strategy: str, default_image_size: int = 224) -> None:
-        super().__init__(vision_backbone_id, image_resize_strategy, default_image_size=default_image_size)
-        if vision_backbone_id not in DINOSigLIP_VISION_BACKBONES:
-            raise ValueError(f"Vision Backbone `{vision_backbone_id}` is not supported on the B200-native path!")
-        if default_image_size != 224:
-            raise ValueError("the B200-native towers are built for 224 px inputs")
-        cfgs = DINOSigLIP_VISION_BACKBONES[vision_backbone_id]
-        self.dino_timm_path_or_url = cfgs["dino"].timm_id
-        self.siglip_timm_path_or_url = cfgs["siglip"].timm_id
-        self.dino_featurizer = VisionTransformer(cfgs["dino"])
-        self.siglip_featurizer = VisionTransformer(cfgs["siglip"])
+    KEYS: Tuple[str, str] = ("dino", "siglip")
+
+    def _build(self, cfgs: Dict[str, VitConfig], image_resize_strategy: str, default_image_size: int) -> None:
+        k0, k1 = self.KEYS
+        for c in cfgs.values():
+            if c.img_size != default_image_size:
+                raise ValueError(f"`{self.identifier}` is registered for {c.img_size} px inputs, got "
+                                 f"default_image_size={default_image_size}")
+        setattr(self, f"{k0}_timm_path_or_url", cfgs[k0].timm_id)
+        setattr(self, f"{k1}_timm_path_or_url", cfgs[k1].timm_id)
+        setattr(self, f"{k0}_featurizer", VisionTransformer(cfgs[k0]))
+        setattr(self, f"{k1}_featurizer", VisionTransformer(cfgs[k1]))
         self.dtype = torch.bfloat16
-        self.dino_data_cfg = {"input_size": (3, 224, 224), "interpolation": "bicubic", "mean": DINO_MEAN,
-                              "std": DINO_STD, "crop_pct": 1.0, "crop_mode": "center"}
-        self.siglip_data_cfg = {"input_size": (3, 224, 224), "interpolation": "bicubic", "mean": SIGLIP_MEAN,
-                                "std": SIGLIP_STD, "crop_pct": 0.9, "crop_mode": "center"}
-        self.image_transform = DinoSigLIPImageTransform(
-            _make_transform(image_resize_strategy, 224, DINO_MEAN, DINO_STD, crop_resize=224),
-            _make_transform(image_resize_strategy, 224, SIGLIP_MEAN, SIGLIP_STD, crop_resize=224),
-        )
+        S = default_image_size
+        for k in self.KEYS:
+            setattr(self, f"{k}_data_cfg", {"input_size": (3, S, S), "interpolation": "bicubic", "mean": cfgs[k].mean,
+                                            "std": cfgs[k].std, "crop_pct": 1.0, "crop_mode": "center"})
+        self.image_transform = self._make_pair_transform(
+            _make_transform(image_resize_strategy, S, cfgs[k0].mean, cfgs[k0].std, crop_resize=S),
+            _make_transform(image_resize_strategy, S, cfgs[k1].mean, cfgs[k1].std, crop_resize=S))
+
+    def _towers(self) -> Tuple["VisionTransformer", "VisionTransformer"]:
+        return getattr(self, f"{self.KEYS[0]}_featurizer"), getattr(self, f"{self.KEYS[1]}_featurizer")
 
     def get_fsdp_wrapping_policy(self) -> Callable:
         return _vit_fsdp_policy()
 
     def forward(self, pixel_values: Dict[str, torch.Tensor]) -> torch.Tensor:
-        dino_px, siglip_px = pixel_values["dino"], pixel_values["siglip"]
-        B = dino_px.shape[0]
-        out = torch.empty((B, NUM_PATCHES, self.embed_dim), dtype=torch.bfloat16, device=dino_px.device)
-        self.dino_featurizer.forward_into(dino_px, out, 0)
-        self.siglip_featurizer.forward_into(siglip_px, out, self.dino_featurizer.embed_dim)
+        t0, t1 = self._towers()
+        px0, px1 = pixel_values[self.KEYS[0]], pixel_values[self.KEYS[1]]
+        B = px0.shape[0]
+        out = torch.empty((B, self.num_patches, self.embed_dim), dtype=torch.bfloat16, device=px0.device)
+        t0.forward_into(px0, out, 0)
+        t1.forward_into(px1, out, t0.embed_dim)
         return out
+
+    @property
+    def default_image_resolution(self) -> Tuple[int, int, int]:
+        return getattr(self, f"{self.KEYS[0]}_data_cfg")["input_size"]
+
+    @property
+    def embed_dim(self) -> int:
+        t0, t1 = self._towers()
+        return t0.embed_dim + t1.embed_dim
+
+    @property
+    def num_patches(self) -> int:
+        return self._towers()[0].cfg.num_patches
+
+    @property
+    def half_precision_dtype(self) -> torch.dtype:
+        return torch.bfloat16
+
+
+class DinoSigLIPViTBackbone(_FusedBackbone):
+    """dinosiglip_vit.py:43-163.  `forward({"dino": [B,3,S,S], "siglip": [B,3,S,S]}) -> [B,P,2176]` (cols 0-1023 DINOv2,
+    1024-2175 SigLIP); `dinosiglip-vit-so-224px` (S 224, P 256) and `dinosiglip-vit-so-384px` (S 384, P 729)."""
+
+    KEYS = ("dino", "siglip")
+
+    def __init__(self, vision_backbone_id: str, image_resize_strategy: str, default_image_size: int = 224) -> None:
+        super().__init__(vision_backbone_id, image_resize_strategy, default_image_size=default_image_size)
+        if vision_backbone_id not in DINOSigLIP_VISION_BACKBONES:
+            raise ValueError(f"Vision Backbone `{vision_backbone_id}` is not supported on the B200-native path!")
+        self._build(DINOSigLIP_VISION_BACKBONES[vision_backbone_id], image_resize_strategy, default_image_size)
+
+    @staticmethod
+    def _make_pair_transform(a, b):
+        return DinoSigLIPImageTransform(a, b)
 
     def preprocess_uint8(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
         """already-resized uint8 frames [B,224,224,3] (HWC, on the GPU) → the `pixel_values` dict in bf16,
         one device kernel for both towers instead of two host-side ToTensor+Normalize passes and a 4x larger H2D copy."""
+        if self.default_image_size != 224:
+            raise ValueError("the LUT preprocessing kernel is built for 224 px frames (use the folded uint8 entry)")
         if getattr(self, "_lut", None) is None or self._lut.device != frames.device:
             self._lut = make_preprocess_lut(frames.device)
         dino, siglip = ops.preprocess_u8(frames, self._lut)
         return {"dino": dino, "siglip": siglip}
 
-    @property
-    def default_image_resolution(self) -> Tuple[int, int, int]:
-        return self.dino_data_cfg["input_size"]
 
-    @property
-    def embed_dim(self) -> int:
-        return self.dino_featurizer.embed_dim + self.siglip_featurizer.embed_dim
+@dataclass
+class DinoCLIPImageTransform:
+    """dinoclip_vit.py:30-37"""
+    dino_image_transform: Callable
+    clip_image_transform: Callable
+    is_prismatic: bool = True
 
-    @property
-    def num_patches(self) -> int:
-        return NUM_PATCHES
+    def __call__(self, img, **kwargs: str) -> Dict[str, torch.Tensor]:
+        return {"dino": self.dino_image_transform(img, **kwargs), "clip": self.clip_image_transform(img, **kwargs)}
 
-    @property
-    def half_precision_dtype(self) -> torch.dtype:
-        return torch.bfloat16
+
+class DinoCLIPViTBackbone(_FusedBackbone):
+    """dinoclip_vit.py:40-147 (`dinoclip-vit-l-336px`): DINOv2 ViT-L/14-reg4 + OpenAI CLIP ViT-L/14-336 (quick-GELU
+    through `override_act_layer`, clip_vit.py:15-27), both on the 336 px frame: `forward({"dino", "clip"}) -> [B,576,2048]`."""
+
+    KEYS = ("dino", "clip")
+
+    def __init__(self, vision_backbone_id: str, image_resize_strategy: str, default_image_size: int = 224) -> None:
+        super().__init__(vision_backbone_id, image_resize_strategy, default_image_size=default_image_size)
+        if vision_backbone_id not in DINOCLIP_VISION_BACKBONES:
+            raise ValueError(f"Vision Backbone `{vision_backbone_id}` is not supported on the B200-native path!")
+        self._build(DINOCLIP_VISION_BACKBONES[vision_backbone_id], image_resize_strategy, default_image_size)
+
+    @staticmethod
+    def _make_pair_transform(a, b):
+        return DinoCLIPImageTransform(a, b)
 
 
 class _SingleTowerBackbone(VisionBackbone):
@@ -569,11 +715,15 @@ class _SingleTowerBackbone(VisionBackbone):
         if vision_backbone_id not in self.REGISTRY:
             raise ValueError(f"Vision Backbone `{vision_backbone_id}` is not supported on the B200-native path!")
         cfg = self.REGISTRY[vision_backbone_id]
+        if cfg.img_size != default_image_size:
+            raise ValueError(f"`{vision_backbone_id}` is registered for {cfg.img_size} px inputs, got "
+                             f"default_image_size={default_image_size}")
         self.timm_path_or_url = cfg.timm_id
         self.dtype = torch.bfloat16
         self.featurizer = VisionTransformer(cfg)
-        self.data_cfg = {"input_size": (3, 224, 224), "mean": self.MEAN, "std": self.STD}
-        self.image_transform = _make_transform(image_resize_strategy, 224, self.MEAN, self.STD, crop_resize=224)
+        S = cfg.img_size
+        self.data_cfg = {"input_size": (3, S, S), "mean": cfg.mean, "std": cfg.std}
+        self.image_transform = _make_transform(image_resize_strategy, S, cfg.mean, cfg.std, crop_resize=S)
 
     def get_fsdp_wrapping_policy(self) -> Callable:
         return _vit_fsdp_policy()
@@ -591,7 +741,7 @@ class _SingleTowerBackbone(VisionBackbone):
 
     @property
     def num_patches(self) -> int:
-        return NUM_PATCHES
+        return self.featurizer.cfg.num_patches
 
     @property
     def half_precision_dtype(self) -> torch.dtype:
@@ -599,7 +749,7 @@ class _SingleTowerBackbone(VisionBackbone):
 
 
 class SigLIPViTBackbone(_SingleTowerBackbone):
-    """siglip_vit.py:8-24 (`siglip-vit-so400m`)."""
+    """siglip_vit.py:8-24 (`siglip-vit-so400m`, `siglip-vit-so400m-384px`)."""
     REGISTRY = SIGLIP_VISION_BACKBONES
     MEAN, STD = SIGLIP_MEAN, SIGLIP_STD
 
@@ -608,6 +758,11 @@ class DinoV2ViTBackbone(_SingleTowerBackbone):
     """dinov2_vit.py:9-19 (`dinov2-vit-l`)."""
     REGISTRY = DINOv2_VISION_BACKBONES
     MEAN, STD = DINO_MEAN, DINO_STD
+
+
+class CLIPViTBackbone(_SingleTowerBackbone):
+    """clip_vit.py:15-27 (`clip-vit-l-336px`: OpenAI weights → quick-GELU override)."""
+    REGISTRY = CLIP_VISION_BACKBONES
 
 
 class PrismaticVisionBackbone(nn.Module):
@@ -636,7 +791,8 @@ class PrismaticVisionBackbone(nn.Module):
             return self.featurizer(pixel_values)
         img, img_fused = torch.split(pixel_values, [3, 3], dim=1)
         B = pixel_values.shape[0]
-        out = torch.empty((B, NUM_PATCHES, self.embed_dim), dtype=torch.bfloat16, device=pixel_values.device)
+        out = torch.empty((B, self.featurizer.cfg.num_patches, self.embed_dim), dtype=torch.bfloat16,
+                          device=pixel_values.device)
         self.featurizer.forward_into(img, out, 0)
         self.fused_featurizer.forward_into(img_fused, out, self.featurizer.embed_dim)
         return out

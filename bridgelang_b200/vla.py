@@ -213,12 +213,13 @@ class OpenVLA(nn.Module):
         emb = self.llm.get_input_embeddings()
         tok = emb(input_ids)                                              # [1, T, llm_dim]
         T, dim = tok.shape[1], tok.shape[2]
-        embeds = torch.empty((1, 1 + NUM_PATCHES + (T - 1), dim), dtype=torch.bfloat16, device=tok.device)
+        n_patch = int(getattr(self.vision_backbone, "num_patches", NUM_PATCHES))   # 256 / 576 / 729
+        embeds = torch.empty((1, 1 + n_patch + (T - 1), dim), dtype=torch.bfloat16, device=tok.device)
         embeds[:, :1] = tok[:, :1]                                        # <BOS>
-        embeds[:, 1 + NUM_PATCHES:] = tok[:, 1:]
+        embeds[:, 1 + n_patch:] = tok[:, 1:]
         # visual prefix, written by fc3's epilogue at token offset 1 (prismatic.py:389-396 splice)
         feats = self.vision_backbone(pixel_values)      # dict (native backbone) or packed [1,6,224,224] (HF twin)
-        self.projector.project(feats, out=embeds, tok_in=NUM_PATCHES, tok_out=embeds.shape[1], tok_shift=1)
+        self.projector.project(feats, out=embeds, tok_in=n_patch, tok_out=embeds.shape[1], tok_shift=1)
         out = self.llm(inputs_embeds=embeds.to(tok.dtype), use_cache=True)
         ids: List[torch.Tensor] = []
         for step in range(max_new_tokens):

@@ -47,11 +47,16 @@ def make_vit_state_dict(cfg: VitConfig, seed: int = 1234, init: str = "stress") 
         sd["cls_token"] = torch.randn(1, 1, D, generator=gen) * (0.02 if stress else 1e-6)
     if cfg.reg_tokens:
         sd["reg_token"] = torch.randn(1, cfg.reg_tokens, D, generator=gen) * (0.02 if stress else 1e-6)
-    sd["pos_embed"] = _tn(gen, 1, NUM_PATCHES, D)          # no_embed_class=True / class_token=False: 256 entries
+    # no_embed_class=True / class_token=False: one row per patch; CLIP (no_embed_class=False): prefix rows as well
+    sd["pos_embed"] = _tn(gen, 1, cfg.num_patches + (0 if cfg.no_embed_class else cfg.n_prefix), D)
     fan_in = 3 * PATCH * PATCH
     bound = 1.0 / fan_in ** 0.5                             # nn.Conv2d default (kaiming_uniform a=sqrt(5))
     sd["patch_embed.proj.weight"] = (torch.rand(D, 3, PATCH, PATCH, generator=gen) * 2 - 1) * bound
-    sd["patch_embed.proj.bias"] = (torch.rand(D, generator=gen) * 2 - 1) * bound
+    patch_bias = (torch.rand(D, generator=gen) * 2 - 1) * bound
+    if cfg.patch_bias:
+        sd["patch_embed.proj.bias"] = patch_bias
+    if cfg.pre_norm:
+        ln("norm_pre")
     for i in range(cfg.depth):
         p = f"blocks.{i}."
         ln(p + "norm1")
@@ -95,10 +100,18 @@ def make_projector_state_dict(fused_dim: int = FUSED_DIM, llm_dim: int = LLM_DIM
     return sd
 
 
-def synthetic_frames(batch: int, seed: int = 0) -> torch.Tensor:
-    """uint8 [B,224,224,3] frames, mirroring vla-scripts/extern/verify_openvla.py:74."""
+def synthetic_frames(batch: int, seed: int = 0, size: int = 224) -> torch.Tensor:
+    """uint8 [B,size,size,3] frames, mirroring vla-scripts/extern/verify_openvla.py:74."""
     gen = torch.Generator().manual_seed(seed)
-    return torch.randint(0, 256, (batch, 224, 224, 3), dtype=torch.uint8, generator=gen)
+    return torch.randint(0, 256, (batch, size, size, 3), dtype=torch.uint8, generator=gen)
+
+
+def normalize_for(cfg: VitConfig, frames_u8: torch.Tensor) -> torch.Tensor:
+    """ToTensor + Normalize with a tower's own mean/std: fp32 [B,3,S,S]."""
+    x = frames_u8.permute(0, 3, 1, 2).to(torch.float32) / 255.0
+    m = torch.tensor(cfg.mean, device=x.device).view(1, 3, 1, 1)
+    s = torch.tensor(cfg.std, device=x.device).view(1, 3, 1, 1)
+    return ((x - m) / s).contiguous()
 
 
 DINO_MEAN, DINO_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # timm data cfg of the DINOv2 checkpoint

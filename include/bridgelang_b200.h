@@ -35,6 +35,7 @@ extern "C" {
 #define BLB_EPI_BIAS_GELU 1 /* out_bf16 = gelu_erf(acc + bias)                         (Mlp.fc1+GELU, projector fc1/fc2) */
 #define BLB_EPI_RESIDUAL 2  /* resid_f32 += gamma*(acc+bias) [+ bf16 copy, row-remapped] (Attention.proj / Mlp.fc2 + LayerScale + add) */
 #define BLB_EPI_PATCH 3     /* resid_f32[remap(row)] = acc + bias + pos[token]          (PatchEmbed + _pos_embed) */
+#define BLB_EPI_BIAS_QGELU 4 /* out_bf16 = quick_gelu(acc + bias)                       (Mlp.fc1 of the OpenAI CLIP towers) */
 
 /* logits dtypes for the decode tail */
 #define BLB_DTYPE_F32 0
@@ -101,14 +102,26 @@ typedef struct blb_vit_weights {
   int32_t patch_ldk;  /* row pitch of patch_w: 592 (588 padded to 16 B) */
   float ln_eps;       /* 1e-6 */
   const void* patch_w;       /* patch_embed.proj.weight as bf16 [D, patch_ldk], k = c*196 + kh*14 + kw */
-  const float* patch_b;      /* [D] */
-  const float* pos_embed;    /* [256, D] */
+  const float* patch_b;      /* [D] or NULL (CLIP: the pre_norm conv has no bias) */
+  const float* pos_embed;    /* [grid*grid, D] position embedding of the PATCH tokens (a checkpoint whose pos_embed also
+                              * covers the class token, timm no_embed_class=False, has that row folded into `prefix`) */
   const float* prefix;       /* [n_prefix, D]: cls_token then reg_token rows, or NULL */
   const blb_block_weights* blocks_host; /* HOST array of n_blocks entries (device pointers inside) */
   int32_t ln_folded;  /* 1: no LayerNorm kernel - norm1/norm2 are folded into the qkv / fc1 GEMMs and their statistics come
                        * from the producing GEMM's epilogue; 0: explicit LayerNorm kernel before qkv / fc1 */
   /* ---- ABI v3 ---- */
   int32_t hidden;     /* unpadded MLP hidden (4096 / 4304): algorithmic FLOP accounting of the timing records; 0 = hidden_pad */
+  int32_t grid;       /* patches per side: 16 (224 px, the default when 0), 24 (336 px), 27 (378 px of a 384 px frame);
+                       * pixels are [batch,3,14*grid,14*grid], tokens = grid*grid + n_prefix, pos_embed is [grid*grid, D] */
+  int32_t img_size;   /* image side in pixels (0 = 14*grid): 384 for the 384 px checkpoints, whose conv ignores the last 6 rows/cols */
+  int32_t act;        /* MLP activation: 0 exact-erf GELU (nn.GELU), 1 quick-GELU x*sigmoid(1.702x) (clip_vit.py:15-27) */
+  const float* norm_pre_w;   /* timm pre_norm=True (OpenAI CLIP): LayerNorm over the embedded tokens (prefix rows included) */
+  const float* norm_pre_b;   /* before block 0; both NULL = identity */
+  /* uint8 entry: patch_embed weight with ToTensor + this tower's Normalize folded in,
+   * W'[n,k] = W[n,c,kh,kw] / (255*std_c) at k = kh*42 + kw*3 + c (HWC patch order), bf16 [D, patch_ldk], and
+   * b'[n] = b[n] - sum_k W[n,c,kh,kw]*mean_c/std_c, fp32 [D].  NULL: the tower has no uint8 entry. */
+  const void* patch_w_u8;
+  const float* patch_b_u8;
 } blb_vit_weights;
 
 /* prismatic/util/nn_utils.py:37-53 FusedMLPProjector == extern/hf/modeling_prismatic.py:146-158 fc1/fc2/fc3 */
@@ -162,6 +175,15 @@ int blb_layernorm(const float* x, int ldx, const float* w, const float* b, void*
 int blb_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int H, int head_dim, void* stream);
 /* timm PatchEmbed staging: pixels bf16 [B,3,224,224] -> bf16 [B*256, ldk], k = c*196+kh*14+kw, zero padded. */
 int blb_im2col_patch14(const void* pixels_bf16, void* cols_bf16, int B, int ldk, void* stream);
+/* same for uint8 HWC frames [B,14*grid,14*grid,3]: -> bf16 [B*grid*grid, ldk] of exact integers 0..255, k = kh*42+kw*3+c
+ * (stride == kernel: im2col is a permutation of the frame; pair with blb_vit_weights.patch_w_u8 / patch_b_u8). */
+int blb_u8_to_patches(const uint8_t* frames_hwc, void* cols_bf16, int B, int ldk, int grid, int img_size, void* stream);
+/* Antialiased resize of uint8 HWC frames [B,Hs,Ws,3] -> [B,Hd,Wd,3], bit-exact with PIL.Image.resize (Pillow's
+ * fixed-point ImagingResample): the Resize of the reference's image transform (dinosiglip_vit.py:91-111,
+ * processing_prismatic.py:128-145 via torchvision).  kx [Wd,ksx] / bx [Wd,2] and ky [Hd,ksy] / by [Hd,2]: int32 device
+ * tables from bridgelang_b200/resize.py (Pillow's precompute_coeffs + normalize_coeffs_8bpc); tmp: Hs*Wd*3*B bytes. */
+int blb_resize_u8(const uint8_t* src, int B, int Hs, int Ws, uint8_t* dst, int Hd, int Wd, const int32_t* kx,
+                  const int32_t* bx, int ksx, const int32_t* ky, const int32_t* by, int ksy, uint8_t* tmp, void* stream);
 
 /* ---- towers, projector, fused path ---------------------------------------------------------------------- */
 size_t blb_vit_workspace_bytes(const blb_vit_weights* w, int batch);
@@ -169,6 +191,11 @@ size_t blb_vit_workspace_bytes(const blb_vit_weights* w, int batch);
  * writes patch tokens (prefix dropped) as bf16 into out[b*256+p, out_col_off : out_col_off+D], pitch ld_out. */
 int blb_vit_tower_forward(const blb_vit_weights* w, const void* pixels_bf16, int batch, void* out_bf16, int ld_out,
                           int out_col_off, void* workspace, size_t workspace_bytes, void* stream);
+
+/* the same from a uint8 HWC frame [batch,14*grid,14*grid,3] (needs patch_w_u8 / patch_b_u8): the patch matrix is built in
+ * the workspace (blb_vit_workspace_bytes covers it) by blb_u8_to_patches and TMA-loaded by the patch-embed GEMM. */
+int blb_vit_tower_forward_u8(const blb_vit_weights* w, const uint8_t* frames_hwc, int batch, void* out_bf16, int ld_out,
+                             int out_col_off, void* workspace, size_t workspace_bytes, void* stream);
 
 size_t blb_projector_workspace_bytes(const blb_projector_weights* w, int rows);
 /* FusedMLPProjector.forward (nn_utils.py:52-53): x bf16 [rows, in_dim] -> out bf16.
@@ -189,6 +216,14 @@ int blb_fused_featurize_project_forward(const blb_vit_weights* dino, const blb_v
                                         const void* pixels_siglip, int batch, void* features_bf16,
                                         void* projected_bf16, void* workspace, size_t workspace_bytes,
                                         void* stream);
+
+/* uint8 entry of the fused path: ONE frame [batch,224,224,3] feeds both towers (their Normalize is folded into
+ * patch_w_u8 / patch_b_u8); workspace: blb_fused_workspace_bytes(...) + blb_patch_matrix_bytes(dino, batch). */
+size_t blb_patch_matrix_bytes(const blb_vit_weights* w, int batch);
+int blb_fused_featurize_project_forward_u8(const blb_vit_weights* dino, const blb_vit_weights* siglip,
+                                           const blb_projector_weights* proj, const uint8_t* frames_hwc, int batch,
+                                           void* features_bf16, void* projected_bf16, void* workspace,
+                                           size_t workspace_bytes, void* stream);
 
 /* ---- rows SURVEY.md section 8f marks "next": the data formats either side of the path ------------------------------ */
 /* Image preprocessing on the device: one uint8 HWC frame [batch,224,224,3] -> both towers' normalized bf16

@@ -17,6 +17,13 @@ timm semantics restated:
   Attention    qkv Linear → [B,N,3,H,hd] → permute(2,0,3,1,4) → SDPA(scale hd^-0.5) → transpose → proj Linear
   Mlp          fc1 → nn.GELU() (exact erf) → fc2;   LayerScale x*gamma (DINOv2 only)
   output       block index depth-2, prefix tokens dropped, final norm NOT applied
+Round 2 (the other fused backbones of materialize.py:48-49):
+  img_size     384 px checkpoints: the strided conv yields floor(384/14) = 27 x 27 patches, the last 6 pixel rows /
+               columns are never read; pos_embed has one row per patch
+  OpenAI CLIP  (clip_vit.py:15-27, `override_act_layer="quick_gelu"`): pre_norm=True → conv WITHOUT bias and a
+               `norm_pre` LayerNorm over all tokens after the embedding; no_embed_class=False → cls is prepended FIRST
+               and pos_embed[1, 1+N, D] is added to every token; quick_gelu(x) = x * sigmoid(1.702 x); no LayerScale.
+               Cross-checked against transformers' CLIPVisionModel (tests/test_oracle_hf_crosscheck.py).
 """
 
 from __future__ import annotations
@@ -45,7 +52,8 @@ def _block(sd: Dict[str, torch.Tensor], p: str, cfg: VitConfig, x: torch.Tensor)
     x = x + h
     # MLP branch (timm Mlp.forward)
     h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS)
-    h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
+    h = F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+    h = h * torch.sigmoid(1.702 * h) if cfg.act == "quick_gelu" else F.gelu(h)
     h = F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
     if cfg.layer_scale:
         h = h * sd[p + "ls2.gamma"]
@@ -54,15 +62,22 @@ def _block(sd: Dict[str, torch.Tensor], p: str, cfg: VitConfig, x: torch.Tensor)
 
 def vit_embed(sd: Dict[str, torch.Tensor], cfg: VitConfig, pixels: torch.Tensor) -> torch.Tensor:
     """timm patch_embed + _pos_embed → [B, tokens, D]."""
-    x = F.conv2d(pixels, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=PATCH)
+    x = F.conv2d(pixels, sd["patch_embed.proj.weight"], sd.get("patch_embed.proj.bias"), stride=PATCH)
     x = x.flatten(2).transpose(1, 2)
-    x = x + sd["pos_embed"]
     prefix = []
     if cfg.class_token:
         prefix.append(sd["cls_token"].expand(x.shape[0], -1, -1))
     if cfg.reg_tokens:
         prefix.append(sd["reg_token"].expand(x.shape[0], -1, -1))
-    return torch.cat(prefix + [x], dim=1) if prefix else x
+    if cfg.no_embed_class:          # timm _pos_embed: position embedding on the patch tokens only, prefix prepended after
+        x = x + sd["pos_embed"]
+        x = torch.cat(prefix + [x], dim=1) if prefix else x
+    else:                           # prefix first, then pos_embed (which has rows for the prefix tokens too)
+        x = torch.cat(prefix + [x], dim=1) if prefix else x
+        x = x + sd["pos_embed"]
+    if cfg.pre_norm:
+        x = F.layer_norm(x, (x.shape[-1],), sd["norm_pre.weight"], sd["norm_pre.bias"], LN_EPS)
+    return x
 
 
 def vit_intermediate(sd: Dict[str, torch.Tensor], cfg: VitConfig, pixels: torch.Tensor,

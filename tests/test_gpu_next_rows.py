@@ -61,7 +61,7 @@ def test_forward_uint8_equals_forward_on_host_normalized_frames():
     proj.load_state_dict(make_projector_state_dict(seed=3))
     enc = blb.VisualPrefixEncoder(bb, proj).cuda()
     frames = synthetic_frames(3, seed=4)
-    a = enc.forward_uint8(frames.cuda())
+    a = enc.forward_uint8(frames.cuda(), folded=False)      # LUT route: bit-identical to the host transform
     b = enc({k: v.to(torch.bfloat16).cuda() for k, v in normalize_frames(frames).items()})
     assert torch.equal(a, b)
 
@@ -127,3 +127,59 @@ def test_hf_processor_device_path_bit_identical():
     got = proc.preprocess_to_device(imgs)
     assert got.shape == (2, 6, 224, 224) and got.dtype == torch.bfloat16
     assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Round 2, SURVEY §8f.2 done properly: mean/std folded into the patch-embed weights, ONE patch-major uint8 matrix
+# feeding both towers (im2col as a permutation, TMA-loaded A operand), coalesced EPI_PATCH stores
+# ---------------------------------------------------------------------------------------------------------------
+def test_u8_to_patches_is_the_hwc_permutation():
+    import torch.nn.functional as F
+    from bridgelang_b200 import ops
+    frames = synthetic_frames(3, seed=4).cuda()
+    cols = ops.u8_to_patches(frames)
+    assert cols.shape == (3 * 256, 592) and cols.dtype == torch.bfloat16
+    # reference: unfold of the NCHW view gives (c, kh, kw) order → reorder to (kh, kw, c)
+    x = frames.permute(0, 3, 1, 2).float()
+    ref = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(3 * 256, 3, 14, 14).permute(0, 2, 3, 1).reshape(-1, 588)
+    assert torch.equal(cols[:, :588].float(), ref) and bool((cols[:, 588:] == 0).all())
+
+
+def test_folded_uint8_entry_matches_the_normalised_path_and_the_oracle():
+    """forward_uint8 (folded patch weights, shared patch matrix) vs forward on the normalised frames vs the fp32
+    oracle: the fold moves the bf16 rounding from the normalised pixel to the weight, so the two native paths agree to
+    bf16 accuracy (not bit for bit) and both sit inside the gate against the oracle."""
+    import bridgelang_b200 as blb
+    from bridgelang_b200.config import DINOV2_L14_REG4, SIGLIP_SO400M_14
+    from bridgelang_b200.weights import make_projector_state_dict, make_vit_state_dict, normalize_frames
+    from oracle import vit_oracle
+    dcfg, scfg = DINOV2_L14_REG4.with_depth(4), SIGLIP_SO400M_14.with_depth(4)
+    dsd, ssd = make_vit_state_dict(dcfg, seed=41, init="stress"), make_vit_state_dict(scfg, seed=42, init="stress")
+    psd = make_projector_state_dict(seed=43)
+    bb = blb.DinoSigLIPViTBackbone("dinosiglip-vit-so-224px", "resize-naive")
+    bb.dino_featurizer, bb.siglip_featurizer = blb.VisionTransformer(dcfg), blb.VisionTransformer(scfg)
+    bb.dino_featurizer.load_state_dict(dsd)
+    bb.siglip_featurizer.load_state_dict(ssd)
+    proj = blb.FusedMLPProjector(2176, 4096)
+    proj.load_state_dict(psd)
+    enc = blb.VisualPrefixEncoder(bb, proj).cuda()
+    frames = synthetic_frames(3, seed=8)
+    px = normalize_frames(frames)
+    ref = vit_oracle.featurize_project(dsd, dcfg, ssd, scfg, psd, px)
+    rel = lambda a, b: ((a.float().cpu() - b.float().cpu()).abs().max() / b.float().cpu().abs().max()).item()
+    out_u8, feats_u8 = enc.forward_uint8(frames.cuda(), return_features=True)
+    out_px = enc({k: v.bfloat16().cuda() for k, v in px.items()})
+    out_lut = enc.forward_uint8(frames.cuda(), folded=False)
+    assert torch.equal(out_lut, out_px)                         # the LUT route is bit-identical to the host transform
+    e_u8, e_px = rel(out_u8, ref), rel(out_px, ref)
+    print(f"uint8 folded {e_u8:.3e}   normalised bf16 {e_px:.3e}   folded vs normalised {rel(out_u8, out_px):.3e}")
+    assert e_u8 < 2e-2 and e_px < 2e-2 and e_u8 < 1.5 * e_px + 1e-3
+    # single-tower uint8 entries
+    d8 = bb.dino_featurizer.forward_uint8(frames.cuda())
+    s8 = bb.siglip_featurizer.forward_uint8(frames.cuda())
+    assert torch.equal(d8, feats_u8[..., :1024]) and torch.equal(s8, feats_u8[..., 1024:])
+    # stream() with uint8 frames uses the folded entry
+    got = list(enc.stream([frames.pin_memory()], uint8=True))
+    assert torch.equal(got[0], out_u8)
+    with pytest.raises(ValueError):
+        enc.forward_uint8(torch.zeros(1, 3, 224, 224, dtype=torch.uint8, device="cuda"))       # CHW is rejected

@@ -205,5 +205,5 @@ def test_stream_double_buffered_equals_per_batch_forward(full_model):
     frames = [synthetic_frames(2, seed=s).pin_memory() for s in (31, 32, 33)]
     got8 = list(enc.stream(frames, uint8=True))
     for g, f in zip(got8, frames):
-        assert torch.equal(g, enc.forward_uint8(f.cuda()))
+        assert torch.equal(g, enc.forward_uint8(f.cuda()))      # the folded uint8 entry
     assert list(enc.stream([])) == []

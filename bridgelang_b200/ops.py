@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_PATCH, EPI_RESIDUAL, Epilogue  # noqa: F401
+from ._lib import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_QGELU, EPI_PATCH, EPI_RESIDUAL, Epilogue  # noqa: F401
 
 
 _WORKSPACES: dict = {}
@@ -86,7 +86,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, mode: int, *, bias=None, gamma=None, 
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
-    if mode in (EPI_BIAS, EPI_BIAS_GELU) and out is None:
+    if mode in (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_QGELU) and out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     e = Epilogue()
     e.bias, e.gamma, e.resid, e.pos = _ptr(bias), _ptr(gamma), _ptr(resid), _ptr(pos)

@@ -8,8 +8,10 @@
 // head_dim 72 is zero-padded to 80 inside shared memory only (the fork needed
 // PT_SDPA_ENABLE_HEAD_DIM_PADDING for it, run_openvla.sh:14).
 //
-// v1 numerics/structure: one CTA per (image, head), 4 warps x 16 query rows per pass, online softmax over
-// 64-key blocks, bf16 mma.sync m16n8k16 with fp32 accumulation.
+// These are the mma.sync kernels for shapes the tcgen05 kernel (attention_tc.cu: the two 224 px tower shapes, every
+// query row) does not take: attention_kernel (short sequences, whole K/V of a head in shared memory: one CTA per
+// (image, head), 4 warps x 16 query rows per pass) and attention_stream_kernel (336 / 384 px towers, K/V streamed).
+// Both: online softmax over 64-key blocks, bf16 mma.sync m16n8k16 with fp32 accumulation.
 #include <cstdlib>
 
 #include <atomic>
@@ -413,229 +415,27 @@ static int launch_attention_stream(const __nv_bfloat16* qkv, __nv_bfloat16* out,
   return static_cast<int>(cudaGetLastError());
 }
 
-// ---- tail kernel: the few query rows beyond the tcgen05 kernel's two 128-row tiles (DINOv2: rows 256..260) -------
-// One CTA per (image, head); its 4 warps SPLIT THE KEYS (16-key blocks) instead of the queries, so every warp is
-// busy although there are only <= 16 query rows: each warp stages only its own <= 80 keys of K and V (cp.async into a
-// private region, warp-level sync only), computes a partial softmax (m, l, O) over them with mma.sync, and the four
-// partials are merged through shared memory (flash-decoding style).  The generic kernel above spent the same launch
-// staging all 320 padded keys per CTA with one warp doing the arithmetic.
-constexpr int TAIL_WARPS = 4;
-constexpr int TAIL_MAXBLK = 5;                 // 16-key blocks per warp → T <= 320
-constexpr int TAIL_PITCH = 64 + 8;             // bf16 elements; +16 B keeps ldmatrix conflict-free
+int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,
+                 int reverse);   // attention_tc.cu
 
-__global__ void __launch_bounds__(TAIL_WARPS * 32)
-attention_tail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H,
-                      float scale_log2, int q_begin, int reverse) {
-  constexpr int HD = 64, PITCH = TAIL_PITCH, KEYS_W = 16 * TAIL_MAXBLK;
-  extern __shared__ __align__(16) uint8_t smem_tail[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_tail);                     // [16][PITCH]
-  __nv_bfloat16* sKV = sQ + 16 * PITCH;                                                // [4 warps][2][KEYS_W][PITCH]
-  float* pm = reinterpret_cast<float*>(sKV + TAIL_WARPS * 2 * KEYS_W * PITCH);         // [4][16] partial row max
-  float* pl = pm + TAIL_WARPS * 16;                                                    // [4][16] partial row sum
-  float* po = pl + TAIL_WARPS * 16;                                                    // [4][16][HD] partial O
-
-  const int unit = reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
-  const int b = unit / H, h = unit % H;
-  const int D = H * HD;
-  const size_t row_pitch = static_cast<size_t>(3) * D;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * row_pitch + h * HD;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_q = T - q_begin;
-  const int nblk = (T + 15) >> 4;
-  const int blk0 = (warp * nblk) / TAIL_WARPS, blk1 = ((warp + 1) * nblk) / TAIL_WARPS;
-  const int my_blocks = blk1 - blk0;
-  const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  __nv_bfloat16* sK = sKV + warp * 2 * KEYS_W * PITCH;
-  __nv_bfloat16* sV = sK + KEYS_W * PITCH;
-  pdl_launch_dependents();
-  pdl_wait();
-
-  // ---- stage: the query rows (all threads) and this warp's keys of K and V (this warp only) ----
-  for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {
-    const int r = i >> 3, c = i & 7;
-    __nv_bfloat16* dq = sQ + r * PITCH + c * 8;
-    if (r < n_q) cp_async16(dq, base + static_cast<size_t>(q_begin + r) * row_pitch + c * 8);
-    else *reinterpret_cast<uint4*>(dq) = zero4;
-  }
-  for (int i = lane; i < my_blocks * 16 * 8; i += 32) {
-    const int r = i >> 3, c = i & 7;
-    const int key = blk0 * 16 + r;
-    __nv_bfloat16* dk = sK + r * PITCH + c * 8;
-    __nv_bfloat16* dv = sV + r * PITCH + c * 8;
-    if (key < T) {
-      const __nv_bfloat16* g = base + static_cast<size_t>(key) * row_pitch + c * 8;
-      cp_async16(dk, g + D);
-      cp_async16(dv, g + 2 * D);
-    } else {
-      *reinterpret_cast<uint4*>(dk) = zero4;
-      *reinterpret_cast<uint4*>(dv) = zero4;
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int g = lane >> 2, t4 = lane & 3;
-  uint32_t qf[4][4];
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(smem_u32(sQ + (lane & 15) * PITCH + ks * 16 + (lane >> 4) * 8), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-
-  // ---- scores of this warp's keys: s[2*blk + half][4] = 16 query rows x 8 keys per n-tile ----
-  float s[2 * TAIL_MAXBLK][4];
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < TAIL_MAXBLK; ++j) {
-    if (j < my_blocks) {
-      float* s0 = s[2 * j];
-      float* s1 = s[2 * j + 1];
-      s0[0] = s0[1] = s0[2] = s0[3] = s1[0] = s1[1] = s1[2] = s1[3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const int key = j * 16 + (lane & 7) + ((lane >> 4) << 3);
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(smem_u32(sK + key * PITCH + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(s[2 * j], qf[ks], b0, b1);
-        mma_bf16_16816(s[2 * j + 1], qf[ks], b2, b3);
-      }
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int key = (blk0 + j) * 16 + hh * 8 + 2 * t4;
-        float* sv = s[2 * j + hh];
-        if (key >= T) sv[0] = sv[2] = -INFINITY;
-        if (key + 1 >= T) sv[1] = sv[3] = -INFINITY;
-        m0 = fmaxf(m0, fmaxf(sv[0], sv[1]));
-        m1 = fmaxf(m1, fmaxf(sv[2], sv[3]));
-      }
-    }
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));   // finite: every warp owns at least one real key
-  const float ms0 = m0 * scale_log2, ms1 = m1 * scale_log2;
-
-  // ---- P = 2^(s·c − m·c), partial sums, partial O = P·V over this warp's keys ----
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < TAIL_MAXBLK; ++j) {
-    if (j < my_blocks) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float* sv = s[2 * j + hh];
-        sv[0] = exp2f(sv[0] * scale_log2 - ms0);
-        sv[1] = exp2f(sv[1] * scale_log2 - ms0);
-        sv[2] = exp2f(sv[2] * scale_log2 - ms1);
-        sv[3] = exp2f(sv[3] * scale_log2 - ms1);
-        l0 += sv[0] + sv[1];
-        l1 += sv[2] + sv[3];
-      }
-      uint32_t pa[4];
-      pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
-      pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
-      pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
-      pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
-      const int key = j * 16 + (lane & 15);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_u32(sV + key * PITCH + p * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * p], pa, b0, b1);
-        mma_bf16_16816(o[2 * p + 1], pa, b2, b3);
-      }
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-  // ---- publish the partials, merge the four key ranges ----
-  if (t4 == 0) {
-    pm[warp * 16 + g] = m0; pm[warp * 16 + g + 8] = m1;
-    pl[warp * 16 + g] = l0; pl[warp * 16 + g + 8] = l1;
-  }
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    float* d0 = po + (warp * 16 + g) * HD + nt * 8 + 2 * t4;
-    float* d1 = po + (warp * 16 + g + 8) * HD + nt * 8 + 2 * t4;
-    d0[0] = o[nt][0]; d0[1] = o[nt][1];
-    d1[0] = o[nt][2]; d1[1] = o[nt][3];
-  }
-  __syncthreads();
-  const int r = threadIdx.x >> 3, c8 = (threadIdx.x & 7) * 8;     // 16 rows x 8 column groups of 8
-  if (r < n_q) {
-    float M = pm[r];
-#pragma unroll
-    for (int w = 1; w < TAIL_WARPS; ++w) M = fmaxf(M, pm[w * 16 + r]);
-    float L = 0.f, acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int w = 0; w < TAIL_WARPS; ++w) {
-      const float f = exp2f((pm[w * 16 + r] - M) * scale_log2);
-      L += pl[w * 16 + r] * f;
-      const float* src = po + (w * 16 + r) * HD + c8;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += src[k] * f;
-    }
-    const float inv = 1.0f / L;
-    uint4 pk;
-    pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-    pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-    pk.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
-    pk.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
-    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + q_begin + r) * D + h * HD + c8) = pk;
-  }
-}
-
-static int launch_attention_tail(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int q_begin,
-                                 cudaStream_t stream, int reverse) {
-  constexpr int KEYS_W = 16 * TAIL_MAXBLK;
-  const int smem = (16 + TAIL_WARPS * 2 * KEYS_W) * TAIL_PITCH * 2 + TAIL_WARPS * 16 * (2 + 64) * 4;
-  static std::atomic<bool> configured[BLB_MAX_DEVICES];
-  if (!configured[current_device()]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured[current_device()] = true;
-  }
-  const float scale_log2 = 1.4426950408889634f / sqrtf(64.0f);
-  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T - q_begin) * T * 64, stream);
-  cudaError_t le = launch_pdl(attention_tail_kernel, dim3(B * H), dim3(TAIL_WARPS * 32), smem, stream, qkv, out, T, H,
-                              scale_log2, q_begin, reverse);
-  if (le != cudaSuccess) return static_cast<int>(le);
-  count_launch(1);
-  return static_cast<int>(cudaGetLastError());
-}
-
-int attention_tc_first256(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd,
-                          cudaStream_t stream, int reverse);   // attention_tc.cu
-
-static bool g_attn_v1_only = getenv("BLB_ATTN_V1") != nullptr;   // A/B switch: mma.sync kernel for everything
+static bool g_attn_v1_only = getenv("BLB_ATTN_V1") != nullptr;   // A/B switch: mma.sync kernels for everything
 
 int attention_bf16(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,
                    int reverse) {
   if (qkv == nullptr || out == nullptr || B <= 0 || T <= 0 || H <= 0) return BLB_ERR_ARG;
   if (hd != 64 && hd != 72) return BLB_ERR_SHAPE;
-  int q_begin = 0;
   if (!g_attn_v1_only) {
-    // tower shapes: the tcgen05 kernel takes query rows [0,256); DINOv2's 5 remaining rows go to the mma.sync kernel
-    const int rc = attention_tc_first256(qkv, out, B, T, H, hd, stream, reverse);
-    if (rc == 0) q_begin = 256;
-    else if (rc != BLB_ERR_SHAPE) return rc;
+    // tower shapes (224 px: 256 / 261 tokens): the tcgen05 kernel takes every query row (DINOv2's 5 rows beyond the two
+    // 128-row tiles are a third tile inside it)
+    const int rc = attention_tc(qkv, out, B, T, H, hd, stream, reverse);
+    if (rc != BLB_ERR_SHAPE) return rc;
   }
-  if (q_begin >= T) return 0;
-  if (q_begin == 0 && T > 320) {   // long sequences (336 / 384 px towers): K/V streamed through shared memory
+  if (T > 320) {   // long sequences (336 / 384 px towers): K/V streamed through shared memory
     if (hd == 64) return launch_attention_stream<64, 64>(qkv, out, B, T, H, stream, reverse);
     return launch_attention_stream<72, 80>(qkv, out, B, T, H, stream, reverse);
   }
-  static const bool tail_generic = getenv("BLB_ATTN_TAIL_GENERIC") != nullptr;   // A/B switch
-  if (hd == 64 && q_begin > 0 && T - q_begin <= 16 && T <= 16 * TAIL_MAXBLK * TAIL_WARPS && !tail_generic)
-    return launch_attention_tail(qkv, out, B, T, H, q_begin, stream, reverse);
-  if (hd == 64) return launch_attention<64, 64>(qkv, out, B, T, H, q_begin, stream, reverse);
-  return launch_attention<72, 80>(qkv, out, B, T, H, q_begin, stream, reverse);
+  if (hd == 64) return launch_attention<64, 64>(qkv, out, B, T, H, 0, stream, reverse);
+  return launch_attention<72, 80>(qkv, out, B, T, H, 0, stream, reverse);
 }
 
 }  // namespace blb

@@ -4,7 +4,11 @@
 //   DINOv2-reg4  T = 261 tokens, head_dim 64   →  template <64, 16>  (256 keys + 16-key tail block, 5 of them real)
 //   SigLIP       T = 256 tokens, head_dim 72   →  template <72, 0>   (d split 64 + 16; the 16-wide block is 32B-swizzled)
 // One persistent CTA per SM walks (image, head) units; per unit it handles the first 256 query rows as two
-// 128-row tiles (the T-256 remaining query rows of DINOv2 go to the mma.sync kernel in attention.cu).
+// 128-row tiles and — DINOv2 only — the T-256 = 5 remaining query rows as a third "tail" tile against the K/V that
+// are already in shared memory (round 1 sent them to a separate mma.sync kernel that re-read all K/V: 274 MB per
+// launch).  The tail tile's Q rows are REPLICATED into all four TMEM lane quarters (four 8-row TMA boxes), so that all
+// eight softmax warps share its 261 score columns (34 each instead of 136 on two warps); every warp zero-fills the P
+// columns it does not own, the four quarters' partial O / row sums are added through shared memory.
 //
 //   warp 8     TMA producer: Q tiles, K, V straight out of the packed QKV GEMM output through a 4-D tensor map
 //              {d, 3·H head slots, token, image}; rows >= T and d >= head_dim are zero-filled by TMA (OOB);
@@ -127,7 +131,11 @@ struct AttnCfg {
   static constexpr int OFF_XCHG = OFF_V + 2 * KV_BYTES;          // partial row maxima [2 tile parities][2 groups][128] (fp32)
   static constexpr int OFF_OST = OFF_XCHG + 4 * QT * 4;          // per-warp [32 rows x 64 B] output staging chunks
   static constexpr int OFF_ONES = OFF_OST + 8 * 2048;            // 512 B of bf16 1.0: the B operand of the row-sum MMAs
-  static constexpr int OFF_BAR = OFF_ONES + 512;
+  // tail tile (KX > 0): partial O [4 quarters][8 rows][64] + partial sums [4][8] + partial maxima [8 warps][32] (fp32)
+  static constexpr int OFF_TAIL = OFF_ONES + 512;
+  static constexpr int TAIL_BYTES = KX > 0 ? (4 * 8 * 64 + 4 * 8 + 8 * 32) * 4 : 0;
+  static constexpr int OFF_BAR = OFF_TAIL + TAIL_BYTES;
+  static constexpr int NT = KX > 0 ? 3 : 2;                      // tiles per (image, head) unit
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   // TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [P_COL, P_COL + (256+KX)/2) | O fp32 [O_COL, O_COL + HDP) |
   //               row sums [SUM_COL, SUM_COL + 16)  (P · ones: every column holds Σ_k P[row, k])
@@ -143,7 +151,7 @@ struct AttnCfg {
 };
 
 struct AttnMaps {
-  CUtensorMap q_main, kv_main, kv_tail, q_x, kv_x;
+  CUtensorMap q_main, kv_main, kv_tail, q_x, kv_x, q_tail;
 };
 
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -181,9 +189,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // named barrier over the 64 threads of one row quarter (softmax warps q and q+4): id 1 + q
 __device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
 
-#ifndef BLB_ATTN_EPI_MODE
-#define BLB_ATTN_EPI_MODE 0
-#endif
 #ifndef BLB_ATTN_PCH
 #define BLB_ATTN_PCH 2
 #endif
@@ -208,6 +213,9 @@ __device__ __forceinline__ float exp2_poly(float t) {
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
 }
 
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
@@ -247,12 +255,13 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
   constexpr int W_TMA = 8, W_MMA = 9, W_ALLOC = 10;
   const int n_units = B * H;
   const int my_units = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int G = 2 * my_units;      // tiles this CTA processes
+  constexpr int NT = Cfg::NT;
+  const int G = NT * my_units;     // tiles this CTA processes
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&maps.q_main);
     tma_prefetch_desc(&maps.kv_main);
-    if (KX > 0) tma_prefetch_desc(&maps.kv_tail);
+    if (KX > 0) { tma_prefetch_desc(&maps.kv_tail); tma_prefetch_desc(&maps.q_tail); }
     if (Cfg::SPLIT_D) { tma_prefetch_desc(&maps.q_x); tma_prefetch_desc(&maps.kv_x); }
   }
   if (warp == W_MMA && lane == 0) {
@@ -292,7 +301,6 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
           const int u = reverse ? n_units - 1 - u_i : u_i;
           const int b = u / H, h = u - b * H;
           const int kb = i & 1;                                          // K/V buffer of this unit
-          const uint32_t ph = static_cast<uint32_t>(i & 1);              // Q barriers: one use per unit
           const uint32_t kph = static_cast<uint32_t>((i >> 1) & 1);      // K/V barriers: one use per two units
           mbar_wait(&k_empty[kb], kph ^ 1u);
           if (elect_one()) {
@@ -303,24 +311,34 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
               tma_load_4d(sK[kb] + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, &k_full[kb], 64, H + h, 0, b);
           }
           __syncwarp();
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&q_empty[t], ph ^ 1u);
+          for (int t = 0; t < NT; ++t) {
+            const int g = i * NT + t, qb = g & 1;                        // Q buffers alternate per tile
+            mbar_wait(&q_empty[qb], static_cast<uint32_t>((g >> 1) & 1) ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(&q_full[t], Cfg::Q_BYTES);
-              tma_load_4d(sQ[t], &maps.q_main, &q_full[t], 0, h, t * QT, b);
-              if (Cfg::SPLIT_D) tma_load_4d(sQ[t] + Cfg::Q_MAIN, &maps.q_x, &q_full[t], 64, h, t * QT, b);
+              if (KX > 0 && t == 2) {
+                // tail tile: query rows 256..263 (rows >= T are zero-filled) into rows 0..7 of every 32-row quarter
+                mbar_expect_tx(&q_full[qb], 4 * 1024);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) tma_load_4d(sQ[qb] + r * 4096, &maps.q_tail, &q_full[qb], 0, h, 2 * QT, b);
+              } else {
+                mbar_expect_tx(&q_full[qb], Cfg::Q_BYTES);
+                tma_load_4d(sQ[qb], &maps.q_main, &q_full[qb], 0, h, t * QT, b);
+                if (Cfg::SPLIT_D) tma_load_4d(sQ[qb] + Cfg::Q_MAIN, &maps.q_x, &q_full[qb], 64, h, t * QT, b);
+              }
             }
             __syncwarp();
+            if (t == 0) {
+              mbar_wait(&v_empty[kb], kph ^ 1u);
+              if (elect_one()) {
+                mbar_expect_tx(&v_full[kb], Cfg::KV_BYTES);
+                tma_load_4d(sV[kb], &maps.kv_main, &v_full[kb], 0, 2 * H + h, 0, b);
+                if (KX > 0) tma_load_4d(sV[kb] + Cfg::KV_MAIN, &maps.kv_tail, &v_full[kb], 0, 2 * H + h, KMAIN, b);
+                if (Cfg::SPLIT_D)
+                  tma_load_4d(sV[kb] + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, &v_full[kb], 64, 2 * H + h, 0, b);
+              }
+              __syncwarp();
+            }
           }
-          mbar_wait(&v_empty[kb], kph ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(&v_full[kb], Cfg::KV_BYTES);
-            tma_load_4d(sV[kb], &maps.kv_main, &v_full[kb], 0, 2 * H + h, 0, b);
-            if (KX > 0) tma_load_4d(sV[kb] + Cfg::KV_MAIN, &maps.kv_tail, &v_full[kb], 0, 2 * H + h, KMAIN, b);
-            if (Cfg::SPLIT_D)
-              tma_load_4d(sV[kb] + Cfg::KV_MAIN + Cfg::KV_TAIL, &maps.kv_x, &v_full[kb], 64, 2 * H + h, 0, b);
-          }
-          __syncwarp();
         }
       }
     } else if (warp == W_MMA) {
@@ -332,14 +350,14 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         constexpr uint32_t idesc_o_x = idesc_bf16(QT, 16, 1);
         // S(g) = Q·Kᵀ into TMEM columns [0, 256+KX)
         auto issue_s = [&](int g) {
-          const int t = g & 1, i = g >> 1, kb = i & 1;
+          const int t = g % NT, i = g / NT, kb = i & 1, qb = g & 1;
           if (t == 0) mbar_wait(&k_full[kb], static_cast<uint32_t>((i >> 1) & 1));
           BLB_TRACE(g - 1, 8);
-          mbar_wait(&q_full[t], static_cast<uint32_t>(i & 1));
+          mbar_wait(&q_full[qb], static_cast<uint32_t>((g >> 1) & 1));
           tc_fence_after();
           BLB_TRACE(g - 1, 9);
           if (elect_one()) {
-            const uint32_t qa = smem_u32(sQ[t]), ka = smem_u32(sK[kb]);
+            const uint32_t qa = smem_u32(sQ[qb]), ka = smem_u32(sK[kb]);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16<1>(tmem_base, make_desc(qa, 1024, 2) + 2 * k, make_desc(ka, 1024, 2) + 2 * k, idesc_s_main,
@@ -354,8 +372,8 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
                              make_desc(ka + Cfg::KV_MAIN, 1024, 2) + 2 * k, idesc_s_tail, k > 0 ? 1u : 0u);
             }
             umma_commit<1>(s_full);
-            umma_commit<1>(&q_empty[t]);
-            if (t == 1) umma_commit<1>(&k_empty[kb]);
+            umma_commit<1>(&q_empty[qb]);
+            if (t == NT - 1) umma_commit<1>(&k_empty[kb]);
           }
           __syncwarp();
         };
@@ -373,7 +391,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
           // issued chunk by chunk as the softmax warps publish P: chunk c = keys [32c, 32c+32) of group 0 and
           // [128+32c, 128+32c+32) of group 1 (+ the 16-key tail block with the last chunk), so that only the last
           // chunk's MMAs are left when the tile's exp2 stream ends
-          const int t = g & 1, i = g >> 1, kb = i & 1;
+          const int t = g % NT, i = g / NT, kb = i & 1;
           const uint32_t ph = static_cast<uint32_t>(g & 1);
           if (t == 0) mbar_wait(&v_full[kb], static_cast<uint32_t>((i >> 1) & 1));
           mbar_wait(o_empty, ph ^ 1u);   // epilogue(g-1) holds O(g-1) in registers
@@ -409,7 +427,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
               umma_commit<1>(&p_empty[c]);
               if (c == PCH - 1) {
                 umma_commit<1>(o_full);
-                if (t == 1) umma_commit<1>(&v_empty[kb]);
+                if (t == NT - 1) umma_commit<1>(&v_empty[kb]);
               }
             }
             __syncwarp();
@@ -453,7 +471,23 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       if (lane == 0) mbar_arrive(o_empty);              // O is in registers: PV(g) may overwrite the accumulator
       BLB_TRACE(gp + 1, 13);
     };
+    float* tail_o = reinterpret_cast<float*>(smem + Cfg::OFF_TAIL);          // [4 quarters][8 rows][64]
+    float* tail_sum = tail_o + 4 * 8 * 64;                                   // [4][8]
+    float* tail_max = tail_sum + 4 * 8;                                      // [8 warps][32 lanes]
     auto epi_stage = [&](int gp) {
+      if (KX > 0 && gp % NT == 2) {
+        // tail tile: this warp holds, for the 8 replicated rows of its quarter, the partial O over the quarter's key
+        // columns (its 32-column half) and the partial row sum → shared memory, combined in epi_store
+        if (lane < 8) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(tail_o + (q * 8 + lane) * 64 + wg * 32 + j) =
+                make_float4(__uint_as_float(o_r[j]), __uint_as_float(o_r[j + 1]), __uint_as_float(o_r[j + 2]),
+                            __uint_as_float(o_r[j + 3]));
+          if (wg == 0) tail_sum[q * 8 + lane] = __uint_as_float(o_sum);
+        }
+        return;
+      }
       const float inv = 1.0f / __uint_as_float(o_sum);
       // the lane's 64-byte row slice → smem (16-byte piece j at j ^ ((row>>1)&3): conflict-free both ways)
 #pragma unroll
@@ -466,7 +500,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         sts128(ob + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk);
       }
       if (Cfg::SPLIT_D && wg == 1) {
-        const int t = gp & 1, i = gp >> 1;
+        const int t = gp % NT, i = gp / NT;
         const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
         const int u = reverse ? n_units - 1 - u_i : u_i;
         const int b = u / H, h = u - b * H;
@@ -481,10 +515,37 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       __syncwarp();
     };
     auto epi_store = [&](int gp) {
-      const int t = gp & 1, i = gp >> 1;
+      const int t = gp % NT, i = gp / NT;
       const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       const int u = reverse ? n_units - 1 - u_i : u_i;
       const int b = u / H, h = u - b * H;
+      if (KX > 0 && t == 2) {
+        asm volatile("bar.sync 6, 256;" ::: "memory");    // every quarter's partials are in shared memory
+        if (q == 0 && lane < T - 2 * QT && lane < 8) {     // warps 0 and 4: one lane per tail row, 32 columns each
+          float tot = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) tot += tail_sum[qq * 8 + lane];
+          const float inv = 1.0f / tot;
+          __nv_bfloat16* dst = out + (static_cast<size_t>(b) * T + 2 * QT + lane) * D + h * HD + wg * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              acc[e] = 0.f;
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) acc[e] += tail_o[(qq * 8 + lane) * 64 + wg * 32 + j + e];
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+            pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+            pk.z = pack_bf16x2(acc[4] * inv, acc[5] * inv);
+            pk.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+            *reinterpret_cast<uint4*>(dst + j) = pk;
+          }
+        }
+        return;
+      }
       __nv_bfloat16* slab = out + (static_cast<size_t>(b) * T + t * QT + q * 32) * D + h * HD + wg * 32;
       uint4 tv[4];
 #pragma unroll
@@ -501,10 +562,80 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       BLB_TRACE(gp + 1, 14);
     };
 
+    // ---- tail tile (KX > 0): 8 replicated query rows per lane quarter, 272 score columns shared by ALL eight warps ----
+    auto tail_tile = [&](int g) {
+      const int wid = wg * 4 + q;                          // which eighth of the keys
+      const int mcol = wg * 128 + q * 32;                  // 32 main score columns of this warp
+      const int tkey0 = KMAIN + wid * 2;                   // + 2 of the 16 tail columns
+      uint32_t tv[32], tx[2];
+      tmem_ld_32x32(lane_addr + mcol, tv);
+      tmem_ld_32x2(lane_addr + tkey0, tx);
+      tmem_ld_wait();
+      reg_fence16(&tv[0]);
+      reg_fence16(&tv[16]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        m0 = fmax3(m0, __uint_as_float(tv[j]), __uint_as_float(tv[j + 1]));
+        m1 = fmax3(m1, __uint_as_float(tv[j + 2]), __uint_as_float(tv[j + 3]));
+      }
+      if (tkey0 < T) m0 = fmaxf(m0, __uint_as_float(tx[0]));
+      if (tkey0 + 1 < T) m1 = fmaxf(m1, __uint_as_float(tx[1]));
+      tail_max[wid * 32 + lane] = fmaxf(m0, m1);
+      asm volatile("bar.sync 5, 256;" ::: "memory");      // all eight warps hold columns of the same rows
+      float m = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, tail_max[w * 32 + lane]);
+      const float ms = m * scale_log2;
+      if (g > 0) {
+#pragma unroll
+        for (int c = 0; c < PCH; ++c) mbar_wait(&p_empty[c], static_cast<uint32_t>((g - 1) & 1));
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 2)
+        pk[j / 2] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(tv[j]), scale_log2, -ms)),
+                                ex2_approx(fmaf(__uint_as_float(tv[j + 1]), scale_log2, -ms)));
+      const float p0 = tkey0 < T ? ex2_approx(fmaf(__uint_as_float(tx[0]), scale_log2, -ms)) : 0.f;
+      const float p1 = tkey0 + 1 < T ? ex2_approx(fmaf(__uint_as_float(tx[1]), scale_log2, -ms)) : 0.f;
+      // P of this quarter's lanes: own 16 packed columns, zeros in the other 48 of this group's half (the partner warp
+      // of the quarter fills the other half), own tail column, zeros in the group's other three
+      const uint32_t zero16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        if (blk == q) tmem_st_32x16(lane_addr + Cfg::P_COL + wg * 64 + blk * 16, pk);
+        else tmem_st_32x16(lane_addr + Cfg::P_COL + wg * 64 + blk * 16, zero16);
+      }
+      uint32_t pt[4];
+      const uint32_t ptail = pack_bf16x2(p0, p1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pt[j] = j == q ? ptail : 0u;
+      tmem_st_32x4(lane_addr + Cfg::P_COL + 128 + wg * 4, pt);
+      if (g > 0) {                                         // the whole epilogue of tile g-1 (a regular tile)
+        epi_load(g - 1);
+        epi_stage(g - 1);
+        epi_store(g - 1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < PCH; ++c) mbar_arrive(&p_full[c]);
+      }
+    };
+
     for (int g = 0; g < G; ++g) {
       mbar_wait(s_full, static_cast<uint32_t>(g & 1));
       tc_fence_after();
       BLB_TRACE(g, 8);
+      if (KX > 0 && g % NT == 2) {
+        tail_tile(g);
+        continue;
+      }
       // ---- this thread's slice of the S row → registers in one pass, then release S ----
       uint32_t sv[Cfg::NREG_S];
 #pragma unroll
@@ -543,17 +674,6 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       // complete; the epilogue of tile g-1 is threaded through the chunks (group 0 one chunk ahead of group 1 where
       // there is room) so that the two warps of a sub-partition are not in their non-MUFU pieces at the same time.
       constexpr int CK = 128 / PCH;
-#if BLB_ATTN_EPI_MODE == 1
-      // the two warps of a sub-partition take turns on the MUFU pipe: group 1 runs the (MUFU-free) epilogue of tile g-1
-      // while group 0 streams its exp2s alone, group 0 does its epilogue while group 1 finishes its exp2s
-      if (g > 0) {
-        epi_load(g - 1);
-        if (wg == 1) {
-          epi_stage(g - 1);
-          epi_store(g - 1);
-        }
-      }
-#endif
 #pragma unroll
       for (int c = 0; c < PCH; ++c) {
         if (g > 0) mbar_wait(&p_empty[c], static_cast<uint32_t>((g - 1) & 1));   // PV(g-1) consumed these P columns
@@ -591,7 +711,6 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
           }
           tmem_st_32x4(lane_addr + Cfg::P_COL + tail_key0 / 2, pt);
         }
-#if BLB_ATTN_EPI_MODE == 0
         if (g > 0) {
           if (c == 0) epi_load(g - 1);
           if (PCH >= 4) {
@@ -603,12 +722,6 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
             if (c == PCH - 1) epi_store(g - 1);
           }
         }
-#else
-        if (g > 0 && wg == 0 && c == PCH - 1) {   // group 0: whole epilogue after its exp2 stream
-          epi_stage(g - 1);
-          epi_store(g - 1);
-        }
-#endif
       }
       tmem_st_wait();               // the last chunk of P is in TMEM
       tc_fence_before();
@@ -676,6 +789,7 @@ int launch_tc_impl(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, i
   if (rc == 0) rc = make_qkv_map(&maps.kv_tail, qkv, B, T, H, HD, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc == 0) rc = make_qkv_map(&maps.q_x, qkv, B, T, H, HD, 16, QT, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc == 0) rc = make_qkv_map(&maps.kv_x, qkv, B, T, H, HD, 16, KMAIN, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc == 0) rc = make_qkv_map(&maps.q_tail, qkv, B, T, H, HD, 64, 8, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != 0) return rc;
   auto kern = attention_tc_kernel<HD, KX, TRACE>;
   static std::atomic<bool> configured[BLB_MAX_DEVICES];   // the attribute is per device
@@ -686,7 +800,7 @@ int launch_tc_impl(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, i
   }
   const int grid = std::min(num_sms(), B * H);
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * 256.0 * T * HD, stream);
+  TimingScope ts(TIME_ATTENTION, 4.0 * B * H * static_cast<double>(T) * T * HD, stream);
   cudaError_t le = launch_pdl(kern, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, stream, maps, out, B, T, H,
                               scale_log2, g_attn_trace, reverse);
   if (le != cudaSuccess) return static_cast<int>(le);
@@ -705,13 +819,14 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H,
 
 void attention_set_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 
-// Handles query rows [0, 256) of every (image, head); returns BLB_ERR_SHAPE when (T, hd) is not one of the two
-// tower configurations this kernel is built for (the caller then uses the mma.sync kernel for everything).
-int attention_tc_first256(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd,
-                          cudaStream_t stream, int reverse) {
+// Handles every query row of the two tower configurations this kernel is built for — T = 256 (hd 64 / 72) and
+// 256 < T <= 264 (hd 64: the 261 tokens of DINOv2-reg4, tail tile of up to 8 rows) — and returns BLB_ERR_SHAPE for
+// anything else (the caller then uses the mma.sync kernels).
+int attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int H, int hd, cudaStream_t stream,
+                 int reverse) {
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) != 0) return BLB_ERR_ALIGN;
   if (hd == 64 && T == 256) return launch_tc<64, 0>(qkv, out, B, T, H, stream, reverse);
-  if (hd == 64 && T > 256 && T <= 272) return launch_tc<64, 16>(qkv, out, B, T, H, stream, reverse);
+  if (hd == 64 && T > 256 && T <= 264) return launch_tc<64, 16>(qkv, out, B, T, H, stream, reverse);
   if (hd == 72 && T == 256) return launch_tc<72, 0>(qkv, out, B, T, H, stream, reverse);
   return BLB_ERR_SHAPE;
 }

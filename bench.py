@@ -213,6 +213,10 @@ def run_gpu(args) -> None:
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.gather and not args.gather_inline and args.gather_mode == "nccl" and args.nccl_max_ctas > 0:
+            # the overlapped all-gather shares the SMs with the towers: a few CTAs move 3.5 GiB in the ~100 ms of a step
+            # with room to spare, more only take SMs and HBM bandwidth from the GEMMs
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_max_ctas))
         dist.init_process_group("nccl", device_id=device)
     if rank == 0:
         build_library()
@@ -257,7 +261,8 @@ def run_gpu(args) -> None:
 
     # --gather: the NCCL all-gather of step i's prefixes runs on a communication stream under the towers of step i+1
     # (PrefixGatherer); --gather-inline keeps it on the compute stream (the round-1 behaviour, for the A/B)
-    gatherer = PrefixGatherer(global_batch) if (args.gather and distributed and not single) else None
+    gatherer = (PrefixGatherer(global_batch, mode=args.gather_mode)
+                if (args.gather and distributed and not single) else None)
     in_flight = [None]
 
     def step_resident():
@@ -480,8 +485,9 @@ def run_gpu(args) -> None:
                        "cache": "no L2 flush needed: per-step working set (1.6 GB weights + >2 GB activations) "
                                 "exceeds the 126 MB L2",
                        "collective": ("none" if gatherer is None else
-                                      "nccl all-gather of prefixes, " + ("in line" if args.gather_inline else
-                                                                         "overlapped with the next step's towers") +
+                                      ("nccl all-gather of prefixes, in line" if args.gather_inline else
+                                       ("peer-memory push (copy engines over NVLink)" if args.gather_mode == "p2p"
+                                        else "nccl all-gather") + " of prefixes, overlapped with the next step's towers") +
                                       f", {2 * 256 * 4096 * (global_batch - B)} bytes received per rank per step")},
             "clocks": clocks,
             "e2e": e2e,
@@ -511,6 +517,10 @@ def main() -> None:
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--gather", action="store_true", help="include the NCCL all-gather of projected prefixes")
     ap.add_argument("--gather-inline", action="store_true", help="with --gather: keep the collective on the compute stream")
+    ap.add_argument("--gather-mode", default="p2p", choices=["p2p", "nccl"],
+                    help="overlapped --gather transport: peer-memory pushes on the copy engines (default) or NCCL")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="--gather-mode nccl: NCCL_MAX_CTAS for the communicator (0 = NCCL's default; measured: fewer is worse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

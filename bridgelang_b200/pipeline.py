@@ -250,12 +250,58 @@ class PrefixGatherer:
     """The same all-gather, taken off the critical path: `launch(local)` enqueues it on a communication stream (which
     waits for the producer of `local`), `wait(handle)` makes the current stream wait for it and returns the gathered
     tensor.  A serving loop calls launch() for step i, encodes step i+1, then wait()s — the 2 MiB per image that cross
-    NVLink (3.5 GiB received per rank at 8 x 256 images, ≈ 5 ms of a ≈ 100 ms step) move under the
-    next step's GEMMs instead of after this step's.  CPU tensors (gloo, the host-logic tests) run in line."""
+    NVLink (3.5 GiB received per rank at 8 x 256 images) move under the next step's GEMMs.
 
-    def __init__(self, global_batch: int, group: Optional[dist.ProcessGroup] = None) -> None:
-        self.global_batch, self.group = global_batch, group
+    mode="p2p" (default on CUDA): every rank PUSHES its shard straight into every peer's gather buffer through NVLink
+    peer memory (`torch.distributed._symmetric_memory`: one symmetric allocation, plain device-to-device copies, i.e.
+    the copy engines) — no SM, no shared-memory and no register footprint next to the towers' persistent kernels, where
+    an NCCL all-gather kernel costs 2.5-4.6 % of the 8-GPU step even when overlapped (profiles/r02_scaling.md).  Two
+    cross-rank barriers bracket the pushes: nobody overwrites a buffer a peer may still be reading, nobody reads before
+    every peer has written.  mode="nccl": `all_gather_into_tensor` on the communication stream.  CPU tensors (gloo, the
+    host-logic tests) run in line."""
+
+    def __init__(self, global_batch: int, group: Optional[dist.ProcessGroup] = None, mode: str = "p2p") -> None:
+        if mode not in ("p2p", "nccl"):
+            raise ValueError("mode must be 'p2p' or 'nccl'")
+        self.global_batch, self.group, self.mode = global_batch, group, mode
         self._stream: Optional[torch.cuda.Stream] = None
+        self._symm = None          # (buffers[2], handles[2], peer views[2][world]) once allocated
+        self._slot = 0
+
+    # -- p2p transport ---------------------------------------------------------------------------------
+    def _symm_buffers(self, local: torch.Tensor, world: int, max_n: int):
+        if self._symm is None:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            shape = (world * max_n, *local.shape[1:])
+            bufs, hdls, views = [], [], []
+            for _ in range(2):     # double-buffered: the consumer reads gather i while gather i+1 is being pushed
+                b = symm.empty(shape, dtype=local.dtype, device=local.device)
+                h = symm.rendezvous(b, grp.group_name)
+                bufs.append(b)
+                hdls.append(h)
+                views.append([h.get_buffer(r, shape, local.dtype) for r in range(world)])
+            self._symm = (bufs, hdls, views)
+        return self._symm
+
+    def _push(self, local: torch.Tensor):
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        sizes, max_n = _gather_layout(self.global_batch, world)
+        lo, hi = sizes[rank]
+        assert local.shape[0] == hi - lo, "local shard does not match shard_bounds()"
+        bufs, hdls, views = self._symm_buffers(local, world, max_n)
+        s = self._slot
+        self._slot ^= 1
+        hdls[s].barrier(channel=0)                       # every rank's consumer is done with slot s (launched 2 gathers ago)
+        src = local.contiguous()
+        for k in range(world):                           # start with the own copy, then walk the ring
+            r = (rank + k) % world
+            views[s][r][rank * max_n: rank * max_n + src.shape[0]].copy_(src, non_blocking=True)
+        hdls[s].barrier(channel=1)                       # every peer's shard has landed in this rank's buffer
+        out = bufs[s]
+        if all(h - l == max_n for l, h in sizes):
+            return out[: self.global_batch]
+        return torch.cat([out[r * max_n: r * max_n + (h - l)] for r, (l, h) in enumerate(sizes)], dim=0)
 
     def launch(self, local: torch.Tensor):
         if not local.is_cuda:
@@ -263,10 +309,13 @@ class PrefixGatherer:
         if self._stream is None or self._stream.device != local.device:
             self._stream = torch.cuda.Stream(local.device)
         produced = torch.cuda.Event()
-        produced.record(torch.cuda.current_stream(local.device))
+        produced.record(torch.cuda.current_stream(local.device))   # also orders the consumer's earlier reads of the slot
         with torch.cuda.stream(self._stream):
             self._stream.wait_event(produced)
-            out = _gather_into(local, self.global_batch, self.group)
+            if self.mode == "p2p":
+                out = self._push(local)
+            else:
+                out = _gather_into(local, self.global_batch, self.group)
             done = torch.cuda.Event()
             done.record(self._stream)
         local.record_stream(self._stream)
@@ -276,5 +325,6 @@ class PrefixGatherer:
         out, done = handle
         if done is not None:
             torch.cuda.current_stream(out.device).wait_event(done)
-            out.record_stream(torch.cuda.current_stream(out.device))
+            if self.mode != "p2p":
+                out.record_stream(torch.cuda.current_stream(out.device))
         return out

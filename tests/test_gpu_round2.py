@@ -192,10 +192,13 @@ for global_batch in (6, 5):                      # even and ragged shards
     local = enc(blb.shard_pixel_values(px, rank, world))
     out = blb.gather_prefixes(local, global_batch)
     assert out.shape == full.shape and torch.equal(out, full), (global_batch, rank)
-    # overlapped variant: the gather of step i runs on a side stream under the encode of step i+1
-    g = blb.PrefixGatherer(global_batch)
-    h1 = g.launch(local); local2 = enc(blb.shard_pixel_values(px, rank, world)); o1 = g.wait(h1)
-    assert torch.equal(o1, full) and torch.equal(local2, local)
+    # overlapped variants: the gather of step i runs on a side stream under the encode of step i+1, as NCCL or as
+    # copy-engine pushes into the peers' symmetric buffers; three rounds exercise the double buffering
+    for mode in ("nccl", "p2p"):
+        g = blb.PrefixGatherer(global_batch, mode=mode)
+        for rnd in range(3):
+            h1 = g.launch(local); local2 = enc(blb.shard_pixel_values(px, rank, world)); o1 = g.wait(h1)
+            assert torch.equal(o1, full) and torch.equal(local2, local), (mode, rnd)
 torch.cuda.synchronize(); dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """

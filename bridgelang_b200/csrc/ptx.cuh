@@ -93,6 +93,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Polite wait for warps with slack (producers, epilogue helpers): a non-blocking test_wait and a nanosleep between
+// polls.  A warp parked in try_wait keeps re-arming it through the sub-partition's MIO queue, the same queue the
+// MUFU instructions of the compute warps go through; a sleeping warp issues nothing.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+template <int NS>
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+#ifdef BLB_BOUNDED_WAIT
+  for (uint32_t polls = 0; !mbar_test_wait(bar, parity); ++polls) {
+    if (polls > static_cast<uint32_t>(BLB_BOUNDED_WAIT)) asm volatile("trap;");
+    __nanosleep(NS);
+  }
+#else
+  while (!mbar_test_wait(bar, parity)) __nanosleep(NS);
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------

@@ -445,7 +445,7 @@ def run_gpu(args) -> None:
                            "flops_per_image": flops_per_image},
             "breakdown_ms_per_step": {k: v["ms"] / 2 for k, v in cats.items()},
             "attention": {
-                "bound": "mufu", "kernel": "attention_tc_kernel (tcgen05 S/PV, softmax exp2 on MUFU.EX2) + DINOv2 tail",
+                "bound": "mufu", "kernel": "attention_tc_kernel (tcgen05 S/PV, softmax exp2 on MUFU.EX2; DINOv2 tail rows as a third tile of the same kernel)",
                 "tflops": att["work"] / (att["ms"] * 1e-3) / 1e12 if att["ms"] > 0 else None,
                 "ms_per_step": att["ms"] / 2, "launches_per_step": att["launches"] // 2,
                 "floor": "16 exp2/clk/SM x 148 SMs (measured: profiles/r02_mufu_bench.log) = 2368 exp2/clk; one exp2 "
@@ -466,6 +466,18 @@ def run_gpu(args) -> None:
             floor_ms = per_img * B / (2368.0 * sm_mhz * 1e6) * 1e3
             roof["attention"].update(exp2_per_step=per_img * B, mufu_floor_ms=floor_ms,
                                      frac=floor_ms / (att["ms"] / 2))
+            # ... and it is about as close to the HBM bound: every launch reads the packed qkv tensor once and writes
+            # the bf16 output once (algorithmic bytes 8·B·T·D per launch; ncu dram bytes agree within 3 %,
+            # profiles/r02_ncu_attention.md) — round 2's diagnostic build without any exp2 is only 14 % faster
+            hbm_bytes = 0
+            for c in ((_D, _S) if not single else (cfg,)):
+                hbm_bytes += c.n_needed_blocks * 8 * B * c.tokens * c.dim
+            hbm_peak = float(peaks.get("hbm_gbs_sustained", peaks.get("hbm_gbs", 6538.0)))
+            hbm_floor_ms = hbm_bytes / (hbm_peak * 1e9) * 1e3
+            roof["attention"].update(hbm_bytes_per_step=hbm_bytes, hbm_gbs=hbm_bytes / (att["ms"] / 2 * 1e-3) / 1e9,
+                                     hbm_peak_gbs=hbm_peak, hbm_floor_ms=hbm_floor_ms,
+                                     hbm_frac=hbm_floor_ms / (att["ms"] / 2))
+            roof["attention"]["bound"] = "mufu + hbm (the two floors are within 20 % of each other)"
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------------
     cpu = None

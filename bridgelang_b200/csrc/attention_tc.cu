@@ -45,7 +45,20 @@ namespace {
 
 constexpr int QT = 128;        // query rows per tile (UMMA M)
 constexpr int KMAIN = 256;     // keys in the main block (UMMA N of S)
-constexpr int TC_THREADS = 512;   // 8 softmax warps + 4 control warps + 4 helper (row max / epilogue) warps
+#ifndef BLB_ATTN_NSG
+#define BLB_ATTN_NSG 2
+#endif
+constexpr int NSG = BLB_ATTN_NSG;   // softmax warpgroups: each owns 256/NSG of the main key columns (NSG warps per sub-partition)
+static_assert(NSG == 2 || NSG == 4, "NSG");
+constexpr int CG = KMAIN / NSG;     // main S columns per softmax group
+constexpr int NSW = 4 * NSG;        // softmax warps
+constexpr int TC_THREADS = 128 * (NSG + 2);   // softmax warpgroups + 4 control warps + 4 helper (row max / epilogue) warps
+// register budgets per thread (setmaxnreg; the three must add up to 512 = 65536 / 128 over all warpgroups)
+constexpr int REG_SOFTMAX = NSG == 2 ? 176 : 88, REG_CONTROL = NSG == 2 ? 56 : 40, REG_HELPER = NSG == 2 ? 104 : 88;
+constexpr int REG_LAUNCH = (65536 / TC_THREADS) / 8 * 8;   // what every thread owns when the kernel starts
+// setmaxnreg moves registers inside the CTA's own allocation (threads x REG_LAUNCH), not the SM's file: an increase
+// beyond it blocks forever
+static_assert(NSG * REG_SOFTMAX + REG_CONTROL + REG_HELPER <= (NSG + 2) * REG_LAUNCH, "register budget");
 
 // ---- descriptors ------------------------------------------------------------------------------------
 // layout_type: 2 = SWIZZLE_128B, 6 = SWIZZLE_32B.  K-major operands: SBO = 8 rows * row_bytes.
@@ -119,6 +132,9 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x2(uint32_t taddr, const uint32_t (&r)[2]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int HD, int KX>
@@ -138,9 +154,9 @@ struct AttnCfg {
   static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;             // [2 unit parities]
   static constexpr int OFF_XCHG = OFF_V + 2 * KV_BYTES;          // scaled row maxima [2 tile parities][128 rows] (fp32), helper → softmax
   static constexpr int OFF_OST = OFF_XCHG + 2 * QT * 4;          // per-helper-warp [32 rows x 128 B] output staging chunks
-  static constexpr int OFF_SUMS = OFF_OST + 4 * 4096;            // partial row sums [2 tile parities][2 groups][128 rows] (fp32), softmax → helper
+  static constexpr int OFF_SUMS = OFF_OST + 4 * 4096;            // partial row sums [2 tile parities][NSG groups][128 rows] (fp32), softmax → helper
   // tail tile (KX > 0): partial O [4 quarters][8 rows][64] + partial sums [4][8] (fp32)
-  static constexpr int OFF_TAIL = OFF_SUMS + 2 * 2 * QT * 4;
+  static constexpr int OFF_TAIL = OFF_SUMS + 2 * NSG * QT * 4;
   static constexpr int TAIL_BYTES = KX > 0 ? (4 * 8 * 64 + 4 * 8) * 4 : 0;
   static constexpr int OFF_BAR = OFF_TAIL + TAIL_BYTES;
   static constexpr int NT = KX > 0 ? 3 : 2;                      // tiles per (image, head) unit
@@ -150,7 +166,7 @@ struct AttnCfg {
   static constexpr int P_COL = S_COLS;
   static constexpr int P_COLS = S_COLS / 2;
   static constexpr int O_COL = P_COL + P_COLS;
-  static constexpr int NREG_S = 128 + KX / 2;                    // S columns one softmax thread keeps in registers
+  static constexpr int NREG_S = CG + KX / 2;                     // S columns one softmax thread keeps in registers (the last group: + keys 256..263)
   static_assert(Q_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0 && KV_MAIN % 1024 == 0, "1 KB aligned blocks");
   static_assert(O_COL + HDP <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
@@ -175,6 +191,11 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N, int FROM>
+__device__ __forceinline__ void setmaxnreg_to() {
+  if constexpr (N > FROM) setmaxnreg_inc<N>();
+  else if constexpr (N < FROM) setmaxnreg_dec<N>();
+}
 
 // Compiler-level fence for registers filled by an asynchronous tcgen05.ld: placed right after tcgen05.wait::ld, it makes
 // every later use of the values depend on a statement that cannot move above the wait (emits no instruction).
@@ -186,24 +207,43 @@ __device__ __forceinline__ void reg_fence8(uint32_t* r) {
   asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
 }
 
+// packed f32x2 arithmetic (sm_100a): one FMA-pipe instruction per two scores
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void ffma2(float& x0, float& x1, uint64_t b, uint64_t c) {   // (x0, x1) = (x0, x1)·b + c
+  asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%0, %1};\n\tfma.rn.f32x2 a, a, %2, %3;\n\tmov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "l"(b), "l"(c));
+}
+__device__ __forceinline__ void fadd2(uint64_t& acc, float p0, float p1) {               // acc += (p0, p1)
+  asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tadd.rn.f32x2 %0, %0, a;\n\t}" : "+l"(acc) : "f"(p0), "f"(p1));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float hsum_f32x2(uint64_t v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+
 // 3-input max (FMNMX3 on sm_100a): halves the instruction count of the row-max pass
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// named barrier over the 64 threads of one row quarter (softmax warps q and q+4): id 1 + q
-__device__ __forceinline__ void pair_barrier(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
-
 #ifndef BLB_ATTN_PCH
 #define BLB_ATTN_PCH 2
 #endif
 constexpr int PCH = BLB_ATTN_PCH;   // P / PV chunks per tile: 128/PCH keys of each group per chunk (4 or 2)
 static_assert(PCH == 4 || PCH == 2, "PCH");
 
-// 2^t for t <= 0 on the FMA pipe (the MUFU pipe, 16 results/clk/SM, is this kernel's ceiling): t = n + f with
-// n = round(t) taken from the low mantissa bits of t + 1.5·2^23 and f in [-0.5, 0.5]; degree-3 minimax fit of 2^f
-// (relative error 7.5e-5 = 1/26 of the bf16 half-ulp that P is rounded to), exponent added with one integer op.
 #ifndef BLB_ATTN_SLEEP_NS
 #define BLB_ATTN_SLEEP_NS 32   // poll interval of the helper / TMA warps' barrier waits (0: park in try_wait like the others)
 #endif
@@ -212,21 +252,12 @@ __device__ __forceinline__ void slack_wait(uint64_t* bar, uint32_t parity) {
   else mbar_wait(bar, parity);
 }
 
-#ifndef BLB_ATTN_POLY_MASK
-#define BLB_ATTN_POLY_MASK 0   // bit i set: element i of every group of four uses exp2_poly instead of MUFU.EX2
-                               // (measured round 2: 8 → -3 %; the softmax warps are short of issue slots, not of MUFU)
+#ifndef BLB_ATTN_DIAG
+#define BLB_ATTN_DIAG 0      // diagnostic builds only: bit 0 drops the exp2s, bit 1 all but one PV MMA per chunk
 #endif
-__device__ __forceinline__ float exp2_poly(float t) {
-  t = fmaxf(t, -126.0f);
-  const float r = t + 12582912.0f;
-  const float f = t - (r - 12582912.0f);
-  float p = 0.0551716685f;
-  p = fmaf(p, f, 0.242611125f);
-  p = fmaf(p, f, 0.693260968f);
-  p = fmaf(p, f, 0.999928057f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
-}
-
+#ifndef BLB_ATTN_STAGGER
+#define BLB_ATTN_STAGGER 0
+#endif
 __device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t (&r)[2]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
@@ -239,41 +270,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out, int B, int T, int H,
                     float scale_log2, long long* trace, int reverse) {
   // trace (debug only, TRACE instantiation): every warp of CTA 0 records clock64() at pipeline events of tiles [8, 16):
-  // trace[((g-8)*16 + warp)*16 + e]; MMA warp e: 0 s_free(g) seen, 1 S(g+1) issued, 2 o_empty seen, 3 PV(g) issued,
+  // trace[((g-8)*32 + warp)*16 + e]; MMA warp e: 0 s_free(g) seen, 1 S(g+1) issued, 2 o_empty seen, 3 PV(g) issued,
   //   4+c p_full[c](g) seen, 8 k_full seen, 9 q_full seen;  softmax warps e: 8 s_full seen, 9 S in registers (s_free),
   //   10 row max read, 4+c P chunk c stored, 12 last P chunk published;  helper warps e: 11 row max of tile g published,
   //   13 O(g) in registers (o_empty), 14 epilogue(g) stores issued
 #define BLB_TRACE(g_, e_)                                                                   \
   do {                                                                                      \
     if (TRACE && trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (g_) >= 8 && (g_) < 16)   \
-      trace[(((g_) - 8) * 16 + (threadIdx.x >> 5)) * 16 + (e_)] = clock64();                                  \
+      trace[(((g_) - 8) * 32 + (threadIdx.x >> 5)) * 16 + (e_)] = clock64();                                  \
   } while (0)
   using Cfg = AttnCfg<HD, KX>;
   extern __shared__ uint8_t smem_raw_attn[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* q_full = bars;         // [2 tiles of a unit]
-  uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* k_full = bars + 4;     // [2 unit parities]
-  uint64_t* k_empty = bars + 6;    // [2]
-  uint64_t* v_full = bars + 8;     // [2]
-  uint64_t* v_empty = bars + 10;   // [2]
-  uint64_t* s_full = bars + 12;    // MMA → softmax + helpers: S(g) is in TMEM
-  uint64_t* s_free = bars + 13;    // softmax (8) + helpers (4) → MMA: every reader of S(g) is done with its TMEM columns
-  uint64_t* o_full = bars + 14;    // MMA → helpers: every PV chunk of tile g has retired
-  uint64_t* o_empty = bars + 15;   // helpers → MMA: O(g) is in registers
-  uint64_t* p_full = bars + 16;    // [PCH] softmax → MMA: P chunk c of tile g is in TMEM
-  uint64_t* p_empty = bars + 16 + PCH;   // [PCH] MMA → softmax: PV chunk c of tile g has consumed its P columns
-  uint64_t* max_full = bars + 16 + 2 * PCH;   // [2 tile parities] helpers → softmax: the scaled row maxima of tile g are in smem
-  uint64_t* sum_full = bars + 18 + 2 * PCH;   // [2 tile parities] softmax → helpers: the partial row sums of tile g are in smem
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + 2 * PCH);
-
-  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  constexpr int W_TMA = 8, W_MMA = 9, W_ALLOC = 10, W_HELP = 12;
-  const int n_units = B * H;
-  const int my_units = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // Values every role needs — the 1 KB-aligned base of the dynamic shared memory, the TMEM base, the CTA's unit count —
+  // live in static shared memory and are READ BACK INSIDE EVERY ROLE BRANCH (volatile loads, so nothing is hoisted):
+  // a value that is live across the setmaxnreg boundaries is allocated against the smallest budget (the control
+  // warps'), gets spilled, and the hot loops then wait for an LDL (an L1-miss round trip: the 227 KB shared-memory
+  // carve-out leaves almost no L1) — ncu attributed ≈ 215 cycles per tile to one such reload.
+  __shared__ uint32_t s_params[4];   // [0] dynamic-smem base (shared-window address), [1] TMEM base, [2] my_units
   constexpr int NT = Cfg::NT;
-  const int G = NT * my_units;     // tiles this CTA processes
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr int W_TMA = NSW, W_MMA = NSW + 1, W_ALLOC = NSW + 2, W_HELP = NSW + 4;
+  const int n_units = B * H;
+
+  // everything a role derives from the shared-memory base (expanded inside each role branch)
+#define BLB_ATTN_ROLE_PROLOGUE                                                                                         \
+  uint8_t* smem;                                                                                                       \
+  uint32_t tmem_base;                                                                                                  \
+  int my_units;                                                                                                        \
+  {                                                                                                                    \
+    uint32_t sb_, mu_;                                                                                                 \
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(sb_) : "r"(smem_u32(&s_params[0])));                                 \
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(smem_u32(&s_params[1])));                           \
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(mu_) : "r"(smem_u32(&s_params[2])));                                 \
+    smem = reinterpret_cast<uint8_t*>(__cvta_shared_to_generic(sb_));                                                  \
+    my_units = static_cast<int>(mu_);                                                                                  \
+  }                                                                                                                    \
+  const int G = NT * my_units;     /* tiles this CTA processes */                                                      \
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);                                             \
+  uint64_t* const q_full = bars;         /* [2 tiles of a unit] */                                                     \
+  uint64_t* const q_empty = bars + 2;    /* [2] */                                                                     \
+  uint64_t* const k_full = bars + 4;     /* [2 unit parities] */                                                       \
+  uint64_t* const k_empty = bars + 6;    /* [2] */                                                                     \
+  uint64_t* const v_full = bars + 8;     /* [2] */                                                                     \
+  uint64_t* const v_empty = bars + 10;   /* [2] */                                                                     \
+  uint64_t* const s_full = bars + 12;    /* MMA → softmax + helpers: S(g) is in TMEM */                                \
+  uint64_t* const s_free = bars + 13;    /* softmax + helpers → MMA: every reader of S(g) is done with its columns */  \
+  uint64_t* const o_full = bars + 14;    /* MMA → helpers: every PV chunk of tile g has retired */                     \
+  uint64_t* const o_empty = bars + 15;   /* helpers → MMA: O(g) is in registers */                                     \
+  uint64_t* const p_full = bars + 16;    /* [PCH] softmax → MMA: P chunk c of tile g is in TMEM */                     \
+  uint64_t* const p_empty = bars + 16 + PCH;       /* [PCH] MMA → softmax: PV chunk c consumed its P columns */        \
+  uint64_t* const max_full = bars + 16 + 2 * PCH;  /* [2 tile parities] helpers → softmax: scaled row maxima in smem */\
+  uint64_t* const sum_full = bars + 18 + 2 * PCH;  /* [2 tile parities] softmax → helpers: partial row sums in smem */ \
+  /* buffer addresses by arithmetic (a dynamically indexed pointer array would live in local memory) */               \
+  auto sQ = [&](int i) { return smem + Cfg::OFF_Q0 + i * Cfg::Q_BYTES; };                                              \
+  auto sK = [&](int i) { return smem + Cfg::OFF_K + i * Cfg::KV_BYTES; };                                              \
+  auto sV = [&](int i) { return smem + Cfg::OFF_V + i * Cfg::KV_BYTES; };                                              \
+  const uint32_t xmax = smem_u32(smem + Cfg::OFF_XCHG);   /* float [2 tile parities][128 rows]: max·scale·log2e */     \
+  const uint32_t psum = smem_u32(smem + Cfg::OFF_SUMS);   /* float [2 parities][NSG groups][128 rows]: Σ_k p */        \
+  (void)G; (void)q_full; (void)q_empty; (void)k_full; (void)k_empty; (void)v_full; (void)v_empty; (void)s_full;        \
+  (void)s_free; (void)o_full; (void)o_empty; (void)p_full; (void)p_empty; (void)max_full; (void)sum_full; (void)sQ;    \
+  (void)sK; (void)sV; (void)xmax; (void)psum
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&maps.q_main);
@@ -282,46 +338,32 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     if (Cfg::SPLIT_D) { tma_prefetch_desc(&maps.q_x); tma_prefetch_desc(&maps.kv_x); }
   }
   if (warp == W_MMA && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&max_full[i], 4);
-      mbar_init(&sum_full[i], 8);
-    }
-    mbar_init(s_full, 1); mbar_init(s_free, 12);
-    mbar_init(o_full, 1); mbar_init(o_empty, 4);
-    for (int c = 0; c < PCH; ++c) { mbar_init(&p_full[c], 8); mbar_init(&p_empty[c], 1); }
+    uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_attn) + 1023) & ~uintptr_t(1023));
+    s_params[0] = smem_u32(smem0);
+    s_params[2] = static_cast<uint32_t>((n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                        static_cast<int>(gridDim.x));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem0 + Cfg::OFF_BAR);
+    for (int i = 0; i < 12; ++i) mbar_init(&bars[i], 1);                 // q/k/v full + empty
+    mbar_init(&bars[12], 1); mbar_init(&bars[13], NSW + 4);              // s_full, s_free
+    mbar_init(&bars[14], 1); mbar_init(&bars[15], 4);                    // o_full, o_empty
+    for (int c = 0; c < PCH; ++c) { mbar_init(&bars[16 + c], NSW); mbar_init(&bars[16 + PCH + c], 1); }   // p_full, p_empty
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars[16 + 2 * PCH + i], 4); mbar_init(&bars[18 + 2 * PCH + i], NSW); }   // max_full, sum_full
     fence_mbar_init();
   }
-  if (warp == W_ALLOC) tmem_alloc<1>(tmem_slot, 512);
+  if (warp == W_ALLOC) tmem_alloc<1>(&s_params[1], 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // every role reads the TMEM base from shared memory inside its own branch: a value that is live across the
-  // setmaxnreg boundaries gets spilled, and the softmax loop then waits for an LDL at the top of every tile
-  auto tmem_base_ld = [&]() {
-    uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(tmem_slot)));
-    return v;
-  };
   pdl_launch_dependents();   // PDL: the prologue above overlapped with the QKV GEMM's tail
   pdl_wait();
 
-  // buffer addresses by arithmetic (a dynamically indexed pointer array would live in local memory: an LDL on the
-  // MMA warp's critical path)
-  auto sQ = [&](int i) { return smem + Cfg::OFF_Q0 + i * Cfg::Q_BYTES; };
-  auto sK = [&](int i) { return smem + Cfg::OFF_K + i * Cfg::KV_BYTES; };
-  auto sV = [&](int i) { return smem + Cfg::OFF_V + i * Cfg::KV_BYTES; };
-  const uint32_t xmax = smem_u32(smem + Cfg::OFF_XCHG);   // float [2 tile parities][128 rows]: max·scale·log2e
-  const uint32_t psum = smem_u32(smem + Cfg::OFF_SUMS);   // float [2 tile parities][2 groups][128 rows]: Σ_k p over the group's keys
   auto lds_f32 = [](uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; };
   auto sts_f32 = [](uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
 
   if (warp >= W_HELP) {
     // ============================ helpers: row max (two tiles ahead) + epilogue =========================
-    setmaxnreg_dec<104>();
-    const uint32_t tmem_base = tmem_base_ld();
+    setmaxnreg_to<REG_HELPER, REG_LAUNCH>();
+    BLB_ATTN_ROLE_PROLOGUE;
     const int q = warp & 3;                              // TMEM lane quarter of this warp
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -386,38 +428,42 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       slack_wait(o_full, static_cast<uint32_t>(g & 1));
       tc_fence_after();
       const uint32_t o_addr = lane_addr + Cfg::O_COL;
-      uint32_t oa[32], ob2[32];
-      tmem_ld_32x32(o_addr, oa);
-      // Σ_k p[row, k]: the two softmax groups' partial sums (fp32, of the unrounded p)
+      // O in 16-column pieces, two loads in flight (the helpers' register budget is small: the softmax warps need it)
+      uint32_t oa[16], ob2[16];
+      tmem_ld_32x16(o_addr, oa);
+      tmem_ld_32x16(o_addr + 16, ob2);
+      // Σ_k p[row, k]: the softmax groups' partial sums (fp32, of the unrounded p)
       slack_wait(&sum_full[g & 1], static_cast<uint32_t>((g >> 1) & 1));
-      const float o_sum = lds_f32(psum + ((g & 1) * 2 * QT + row) * 4) + lds_f32(psum + ((g & 1) * 2 * QT + QT + row) * 4);
+      float o_sum = 0.f;
+#pragma unroll
+      for (int sg = 0; sg < NSG; ++sg) o_sum += lds_f32(psum + (((g & 1) * NSG + sg) * QT + row) * 4);
       tmem_ld_wait();
-      reg_fence16(&oa[0]); reg_fence16(&oa[16]);
-      tmem_ld_32x32(o_addr + 32, ob2);
+      reg_fence16(oa); reg_fence16(ob2);
       if (KX > 0 && t == 2) {
         // tail tile: this quarter's lanes 0-7 hold, for the 8 replicated rows, the partial O / partial row sum over
-        // the key columns that softmax warps q and q+4 own → shared memory, combined below by all four helper warps
-        if (lane < 8) {
+        // the key columns that the softmax warps of quarter q own → shared memory, combined below by all four helpers
+        auto put16 = [&](const uint32_t (&v)[16], int c0) {
+          if (lane < 8) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(tail_o + (q * 8 + lane) * 64 + j) =
-                make_float4(__uint_as_float(oa[j]), __uint_as_float(oa[j + 1]), __uint_as_float(oa[j + 2]),
-                            __uint_as_float(oa[j + 3]));
-          tail_sum[q * 8 + lane] = o_sum;
-        }
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(tail_o + (q * 8 + lane) * 64 + c0 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                              __uint_as_float(v[j + 3]));
+          }
+        };
+        put16(oa, 0);
+        put16(ob2, 16);
+        if (lane < 8) tail_sum[q * 8 + lane] = o_sum;
+        tmem_ld_32x16(o_addr + 32, oa);
+        tmem_ld_32x16(o_addr + 48, ob2);
         tmem_ld_wait();
-        reg_fence16(&ob2[0]); reg_fence16(&ob2[16]);
+        reg_fence16(oa); reg_fence16(ob2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);              // O is in registers: PV(g+1) may overwrite the accumulator
         BLB_TRACE(g, 13);
-        if (lane < 8) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(tail_o + (q * 8 + lane) * 64 + 32 + j) =
-                make_float4(__uint_as_float(ob2[j]), __uint_as_float(ob2[j + 1]), __uint_as_float(ob2[j + 2]),
-                            __uint_as_float(ob2[j + 3]));
-        }
+        put16(oa, 32);
+        put16(ob2, 48);
         asm volatile("bar.sync 1, 128;" ::: "memory");    // the four quarters' partials are in shared memory
         const int tid = q * 32 + lane, r = tid >> 4, c4 = (tid & 15) * 4;   // 8 rows x 16 groups of 4 columns
         if (r < T - 2 * QT) {
@@ -439,33 +485,32 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       }
       const float inv = 1.0f / o_sum;
       // the lane's 128-byte row → smem staging (16-byte piece j at j ^ (row & 7): conflict-free both ways)
+      auto stage16 = [&](const uint32_t (&v)[16], int piece0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(oa[8 * j]) * inv, __uint_as_float(oa[8 * j + 1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(oa[8 * j + 2]) * inv, __uint_as_float(oa[8 * j + 3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(oa[8 * j + 4]) * inv, __uint_as_float(oa[8 * j + 5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(oa[8 * j + 6]) * inv, __uint_as_float(oa[8 * j + 7]) * inv);
-        sts128(ob + lane * 128 + ((j ^ (lane & 7)) << 4), pk);
-      }
+        for (int j = 0; j < 2; ++j) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+          pk.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+          pk.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+          pk.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+          sts128(ob + lane * 128 + (((piece0 + j) ^ (lane & 7)) << 4), pk);
+        }
+      };
+      stage16(oa, 0);
+      stage16(ob2, 2);
       uint32_t ox[Cfg::SPLIT_D ? 8 : 1];
+      tmem_ld_32x16(o_addr + 32, oa);
+      tmem_ld_32x16(o_addr + 48, ob2);
       if (Cfg::SPLIT_D) tmem_ld_32x8(o_addr + 64, reinterpret_cast<uint32_t(&)[8]>(ox[0]));   // d 64..71 (72..79: padding)
       tmem_ld_wait();
-      reg_fence16(&ob2[0]); reg_fence16(&ob2[16]);
+      reg_fence16(oa); reg_fence16(ob2);
       if (Cfg::SPLIT_D) reg_fence8(&ox[0]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);                // O is in registers: PV(g+1) may overwrite the accumulator
       BLB_TRACE(g, 13);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 pk;
-        pk.x = pack_bf16x2(__uint_as_float(ob2[8 * j]) * inv, __uint_as_float(ob2[8 * j + 1]) * inv);
-        pk.y = pack_bf16x2(__uint_as_float(ob2[8 * j + 2]) * inv, __uint_as_float(ob2[8 * j + 3]) * inv);
-        pk.z = pack_bf16x2(__uint_as_float(ob2[8 * j + 4]) * inv, __uint_as_float(ob2[8 * j + 5]) * inv);
-        pk.w = pack_bf16x2(__uint_as_float(ob2[8 * j + 6]) * inv, __uint_as_float(ob2[8 * j + 7]) * inv);
-        sts128(ob + lane * 128 + (((4 + j) ^ (lane & 7)) << 4), pk);
-      }
+      stage16(oa, 4);
+      stage16(ob2, 6);
       __nv_bfloat16* slab = out + (static_cast<size_t>(b) * T + t * QT + q * 32) * D + h * HD;
       if (Cfg::SPLIT_D) {
         uint4 pk;
@@ -494,15 +539,18 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
 
     if (G > 0) row_max(0);
     if (G > 1) row_max(1);
+#pragma unroll 1
     for (int g = 0; g < G; ++g) {
       epilogue(g);
       if (g + 2 < G) row_max(g + 2);
     }
-  } else if (warp >= 8) {
-    setmaxnreg_dec<56>();          // hand registers to the softmax warps
+  } else if (warp >= NSW) {
+    setmaxnreg_to<REG_CONTROL, REG_LAUNCH>();          // hand registers to the softmax warps
     if (warp == W_TMA) {
       // ============================== TMA producer (warp-uniform loop, one elected lane issues) ===========
       {
+        BLB_ATTN_ROLE_PROLOGUE;
+        (void)tmem_base;
         for (int i = 0; i < my_units; ++i) {
           const int u_i = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
           const int u = reverse ? n_units - 1 - u_i : u_i;
@@ -551,7 +599,7 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     } else if (warp == W_MMA) {
       // =============================== MMA issuer (warp-uniform loop, one elected lane issues) ===========
       {
-        const uint32_t tmem_base = tmem_base_ld();
+        BLB_ATTN_ROLE_PROLOGUE;
         constexpr uint32_t idesc_s_main = idesc_bf16(QT, KMAIN, 0);
         constexpr uint32_t idesc_s_tail = idesc_bf16(QT, 16, 0);
         constexpr uint32_t idesc_o_main = idesc_bf16(QT, 64, 1);
@@ -596,9 +644,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
             BLB_TRACE(g, 1);
           }
           // ---------------- O(g) = P(g) · V   (A = P in TMEM, B = V as an MN-major smem operand) ----------------
-          // issued chunk by chunk as the softmax warps publish P: chunk c = keys [64c, 64c+64) of group 0 and
-          // [128+64c, 128+64c+64) of group 1 (+ the 16-key tail block with the last chunk), so that only the last
-          // chunk's MMAs are left when the tile's exp2 stream ends
+          // issued chunk by chunk as the softmax warps publish P: chunk c = keys [CG/PCH·c, CG/PCH·(c+1)) of every
+          // group's CG columns (+ the 16-key tail block with the last chunk), so that only the last chunk's MMAs are
+          // left when the tile's exp2 stream ends
           const int t = g % NT, i = g / NT, kb = i & 1;
           const uint32_t ph = static_cast<uint32_t>(g & 1);
           if (t == 0) mbar_wait(&v_full[kb], static_cast<uint32_t>((i >> 1) & 1));
@@ -617,10 +665,11 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
             tc_fence_after();
             BLB_TRACE(g, 4 + c);
             if (elect_one()) {
-              constexpr int MPG = 8 / PCH;         // 16-key MMAs per group and chunk
+              constexpr int KBG = CG / 16;         // 16-key blocks per softmax group
+              constexpr int MPG = KBG / PCH;       // 16-key MMAs per group and chunk
 #pragma unroll
-              for (int jj = 0; jj < 2 * MPG; ++jj) {   // 16 keys per MMA: 8 packed P columns, V rows 16j..16j+15
-                const int j = (jj / MPG) * 8 + MPG * c + (jj % MPG);
+              for (int jj = 0; jj < ((BLB_ATTN_DIAG & 2) ? 1 : NSG * MPG); ++jj) {   // 16 keys per MMA: 8 packed P columns, V rows 16j..16j+15
+                const int j = (jj / MPG) * KBG + MPG * c + (jj % MPG);
                 umma_bf16_ts(o_col, p_col + j * 8, vdesc + static_cast<uint64_t>(j * 128), idesc_o_main,
                              (c | jj) != 0 ? 1u : 0u);
                 if (Cfg::SPLIT_D)
@@ -643,40 +692,46 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
     }
   } else {
     // ============================ softmax: pull S, exp2, pack, publish P — nothing else ==================
-    // 8 warps: group wg = 0/1 owns S columns [128·wg, 128·wg+128) plus 8 of the 16 tail columns; both groups see
-    // all 128 rows (warps w and w+4 share TMEM lane quarter w%4), i.e. two softmax warps per SM sub-partition.
-    setmaxnreg_inc<176>();
-    const uint32_t tmem_base = tmem_base_ld();
+    // 4·NSG warps: group wg owns S columns [CG·wg, CG·wg+CG) (the last group also keys 256..263 of the tail block);
+    // every group sees all 128 rows (warps w, w+4, ... share TMEM lane quarter w%4), i.e. NSG softmax warps per SM
+    // sub-partition: while one of them is in a MUFU-free piece (S pull, barrier waits, the last store's completion)
+    // the others keep the MUFU pipe busy.
+    setmaxnreg_to<REG_SOFTMAX, REG_LAUNCH>();
+    BLB_ATTN_ROLE_PROLOGUE;
     const int q = warp & 3;
     const int wg = warp >> 2;
     const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int col_base = wg * 128;
-    const int tail_key0 = KMAIN + wg * 8;                // first key of this group's 8 tail columns
+    const int col_base = wg * CG;
+    const bool has_tail = KX > 0 && wg == NSG - 1;       // this group also owns keys 256..263 (264..271 are always padding)
 
-    // ---- tail tile (KX > 0): 8 replicated query rows per lane quarter, 272 score columns shared by ALL eight warps ----
+    // ---- tail tile (KX > 0): 8 replicated query rows per lane quarter, 272 score columns shared by ALL softmax warps ----
     auto tail_tile = [&](int g) {
-      const int wid = wg * 4 + q;                          // which eighth of the keys
-      const int mcol = wg * 128 + q * 32;                  // 32 main score columns of this warp
-      const int tkey0 = KMAIN + wid * 2;                   // + 2 of the 16 tail columns
-      uint32_t tv[32], tx[2];
-      tmem_ld_32x32(lane_addr + mcol, tv);
-      tmem_ld_32x2(lane_addr + tkey0, tx);
+      constexpr int MC = KMAIN / NSW;                      // main score columns per warp: 32 | 16
+      constexpr int TK = 16 / NSW;                         // tail-block keys per warp: 2 | 1
+      const int wid = wg * 4 + q;                          // which slice of the keys
+      const int mcol = wg * CG + q * MC;
+      const int tkey0 = KMAIN + wid * TK;
+      uint32_t tv[MC], tx[2];
+      if constexpr (MC == 32) tmem_ld_32x32(lane_addr + mcol, reinterpret_cast<uint32_t(&)[32]>(tv[0]));
+      else tmem_ld_32x16(lane_addr + mcol, reinterpret_cast<uint32_t(&)[16]>(tv[0]));
+      if constexpr (TK == 2) tmem_ld_32x2(lane_addr + tkey0, tx);
+      else { tmem_ld_32x1(lane_addr + tkey0, tx[0]); tx[1] = 0u; }
       tmem_ld_wait();
-      reg_fence16(&tv[0]);
-      reg_fence16(&tv[16]);
+#pragma unroll
+      for (int c = 0; c < MC / 8; ++c) reg_fence8(&tv[c * 8]);
       asm volatile("" : "+r"(tx[0]), "+r"(tx[1]));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
       mbar_wait(&max_full[g & 1], static_cast<uint32_t>((g >> 1) & 1));
       const float ms = lds_f32(xmax + ((g & 1) * QT + row) * 4);
-      uint32_t pk[16];
+      uint32_t pk[MC / 2];
       const float p0 = tkey0 < T ? ex2_approx(fmaf(__uint_as_float(tx[0]), scale_log2, -ms)) : 0.f;
-      const float p1 = tkey0 + 1 < T ? ex2_approx(fmaf(__uint_as_float(tx[1]), scale_log2, -ms)) : 0.f;
+      const float p1 = (TK == 2 && tkey0 + 1 < T) ? ex2_approx(fmaf(__uint_as_float(tx[1]), scale_log2, -ms)) : 0.f;
       float l0 = p0, l1 = p1;
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
+      for (int j = 0; j < MC; j += 2) {
         const float e0 = ex2_approx(fmaf(__uint_as_float(tv[j]), scale_log2, -ms));
         const float e1 = ex2_approx(fmaf(__uint_as_float(tv[j + 1]), scale_log2, -ms));
         pk[j / 2] = pack_bf16x2(e0, e1);
@@ -687,23 +742,39 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
         for (int c = 0; c < PCH; ++c) mbar_wait(&p_empty[c], static_cast<uint32_t>((g - 1) & 1));
         tc_fence_after();
       }
-      // the partial sum over this warp's key columns; the helper of quarter q adds the two groups' partials, exactly
+      // the partial sum over this warp's key columns; the helper of quarter q adds the groups' partials, exactly
       // the keys its quarter's partial O covers.  (Written after the p_empty waits: PV(g-1) issued ⇒ the helpers have
       // read the sums of tile g-2, which used this slot.)
-      sts_f32(psum + ((g & 1) * 2 * QT + wg * QT + row) * 4, l0 + l1);
-      // P of this quarter's lanes: own 16 packed columns, zeros in the other 48 of this group's half (the partner warp
-      // of the quarter fills the other half), own tail column, zeros in the group's other three
+      sts_f32(psum + (((g & 1) * NSG + wg) * QT + row) * 4, l0 + l1);
+      // P of this quarter's lanes: own MC/2 packed columns, zeros in the other three blocks of this group's CG/2 (the
+      // partner warps of the quarter fill the other groups' columns), own tail key, zeros in the rest of the group's
+      // share of the 8 packed tail columns
       const uint32_t zero16[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
-        if (blk == q) tmem_st_32x16(lane_addr + Cfg::P_COL + wg * 64 + blk * 16, pk);
-        else tmem_st_32x16(lane_addr + Cfg::P_COL + wg * 64 + blk * 16, zero16);
+        const uint32_t pa = lane_addr + Cfg::P_COL + wg * (CG / 2) + blk * (MC / 2);
+        if constexpr (MC == 32) {
+          if (blk == q) tmem_st_32x16(pa, reinterpret_cast<const uint32_t(&)[16]>(pk[0]));
+          else tmem_st_32x16(pa, zero16);
+        } else {
+          if (blk == q) tmem_st_32x8(pa, reinterpret_cast<const uint32_t(&)[8]>(pk[0]));
+          else tmem_st_32x8(pa, reinterpret_cast<const uint32_t(&)[8]>(zero16[0]));
+        }
       }
-      uint32_t pt[4];
-      const uint32_t ptail = pack_bf16x2(p0, p1);
+      if constexpr (TK == 2) {
+        uint32_t pt[4];
+        const uint32_t ptail = pack_bf16x2(p0, p1);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pt[j] = j == q ? ptail : 0u;
-      tmem_st_32x4(lane_addr + Cfg::P_COL + 128 + wg * 4, pt);
+        for (int j = 0; j < 4; ++j) pt[j] = j == q ? ptail : 0u;
+        tmem_st_32x4(lane_addr + Cfg::P_COL + 128 + wg * 4, pt);
+      } else {
+        // key 256 + 4·wg + q lives in packed column 2·wg + (q >> 1), low or high half by q & 1
+        uint32_t pt[2];
+        const uint32_t ptail = (q & 1) ? pack_bf16x2(0.f, p0) : pack_bf16x2(p0, 0.f);
+        pt[0] = (q >> 1) == 0 ? ptail : 0u;
+        pt[1] = (q >> 1) == 1 ? ptail : 0u;
+        tmem_st_32x2(lane_addr + Cfg::P_COL + 128 + wg * 2, pt);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -725,9 +796,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       // ---- this thread's slice of the S row → registers in one pass, then release S ----
       uint32_t sv[Cfg::NREG_S];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < CG / 32; ++c)
         tmem_ld_32x32(lane_addr + col_base + c * 32, reinterpret_cast<uint32_t(&)[32]>(sv[c * 32]));
-      if (KX > 0) tmem_ld_32x8(lane_addr + tail_key0, reinterpret_cast<uint32_t(&)[8]>(sv[128]));
+      if (has_tail) tmem_ld_32x8(lane_addr + KMAIN, reinterpret_cast<uint32_t(&)[8]>(sv[KX > 0 ? CG : 0]));
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < Cfg::NREG_S / 8; ++c) reg_fence8(&sv[c * 8]);
@@ -735,33 +806,61 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);
       BLB_TRACE(g, 9);
+#if BLB_ATTN_STAGGER > 0
+      // One-time phase shift of the odd groups against the even ones (cycles); nothing re-synchronises the groups
+      // afterwards: the shared barriers only bound the lead of one group over another (to roughly a tile).
+      if (g == 0 && (wg & 1)) {
+        const long long t_st = clock64();
+        while (clock64() - t_st < BLB_ATTN_STAGGER) {
+        }
+      }
+#endif
       // ---- the row max (times scale·log2e) comes from the helper warps, computed while the previous tile ran ----
       mbar_wait(&max_full[g & 1], static_cast<uint32_t>((g >> 1) & 1));
       const float ms = lds_f32(xmax + ((g & 1) * QT + row) * 4);
       BLB_TRACE(g, 10);
-      // ---- p = 2^(s*c - m*c) → bf16 P → TMEM in PCH chunks (CK keys = CK/2 packed columns each); the row sum is an
-      // MMA.  Chunk c is published (p_full[c]) one chunk late, after its tcgen05.st had a whole chunk of exp2s to
-      // complete.
-      constexpr int CK = 128 / PCH;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // this thread's partial row sum (fp32, four independent chains)
+      // ---- p = 2^(s*c - m*c) → bf16 P → TMEM in PCH chunks (CK keys = CK/2 packed columns each).  A chunk is
+      // published (p_full[c]) one 16-key sub-block into the next chunk: its tcgen05.st has completed by then.
+      constexpr int CK = CG / PCH;
+      static_assert(CK == 64 || CK == 32 || CK == 16, "chunk size");
+      float l0 = 0.f, l1 = 0.f;                         // this thread's partial row sum: tail keys ...
+      uint64_t l01 = 0ull, l23 = 0ull;                   // ... and two packed f32x2 chains over the main columns
+      const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2), nms2 = pack_f32x2(-ms, -ms);
+      uint32_t pt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // packed tail columns (keys 256..271), last group only
+      if (has_tail) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float p0 = (KMAIN + j < T) ? ex2_approx(fmaf(__uint_as_float(sv[(KX > 0 ? CG : 0) + j]), scale_log2, -ms)) : 0.f;
+          const float p1 =
+              (KMAIN + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(sv[(KX > 0 ? CG : 0) + j + 1]), scale_log2, -ms)) : 0.f;
+          pt[j / 2] = pack_bf16x2(p0, p1);
+          l0 += p0; l1 += p1;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < PCH; ++c) {
         uint32_t pk[CK / 2];
+        // packed f32x2 arithmetic (sm_100: FFMA2 / FADD2): the scale-and-shift and the row sum cost one instruction per
+        // TWO scores.  A warp issues in order and ptxas groups a chunk into [FFMAs][MUFUs][packs, adds] (it does not
+        // keep an interleaved asm order), so every FMA-pipe instruction of the softmax warps is a cycle in which none of
+        // the sub-partition's softmax warps feeds the MUFU pipe: fewer of them is the lever.
 #pragma unroll
         for (int sb = 0; sb < CK / 16; ++sb) {            // sub-blocks of 16 keys
 #pragma unroll
           for (int j = sb * 16; j < sb * 16 + 16; j += 4) {
-            const float t0 = fmaf(__uint_as_float(sv[c * CK + j]), scale_log2, -ms);
-            const float t1 = fmaf(__uint_as_float(sv[c * CK + j + 1]), scale_log2, -ms);
-            const float t2 = fmaf(__uint_as_float(sv[c * CK + j + 2]), scale_log2, -ms);
-            const float t3 = fmaf(__uint_as_float(sv[c * CK + j + 3]), scale_log2, -ms);
-            const float p0 = (BLB_ATTN_POLY_MASK & 1) ? exp2_poly(t0) : ex2_approx(t0);
-            const float p1 = (BLB_ATTN_POLY_MASK & 2) ? exp2_poly(t1) : ex2_approx(t1);
-            const float p2 = (BLB_ATTN_POLY_MASK & 4) ? exp2_poly(t2) : ex2_approx(t2);
-            const float p3 = (BLB_ATTN_POLY_MASK & 8) ? exp2_poly(t3) : ex2_approx(t3);
+            float t0 = __uint_as_float(sv[c * CK + j]), t1 = __uint_as_float(sv[c * CK + j + 1]);
+            float t2 = __uint_as_float(sv[c * CK + j + 2]), t3 = __uint_as_float(sv[c * CK + j + 3]);
+            ffma2(t0, t1, sc2, nms2);
+            ffma2(t2, t3, sc2, nms2);
+#if BLB_ATTN_DIAG & 1   // diagnostic build (wrong numerics): no MUFU in the main loop — is the tile MUFU-bound at all?
+            const float p0 = t0 * 0.5f, p1 = t1 * 0.5f, p2 = t2 * 0.5f, p3 = t3 * 0.5f;
+#else
+            const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
+#endif
             pk[j / 2] = pack_bf16x2(p0, p1);
             pk[j / 2 + 1] = pack_bf16x2(p2, p3);
-            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            fadd2(l01, p0, p1);
+            fadd2(l23, p2, p3);
           }
           if (c > 0 && sb == 0) {     // publish the previous chunk: its store was issued a sub-block of exp2s ago
             tmem_st_wait();
@@ -774,25 +873,14 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
           mbar_wait(&p_empty[c], static_cast<uint32_t>((g - 1) & 1));
           tc_fence_after();
         }
-        if constexpr (CK == 32) tmem_st_32x16(lane_addr + Cfg::P_COL + (col_base + c * CK) / 2, pk);
-        else tmem_st_32x32(lane_addr + Cfg::P_COL + (col_base + c * CK) / 2, pk);
+        const uint32_t pa = lane_addr + Cfg::P_COL + (col_base + c * CK) / 2;
+        if constexpr (CK == 64) tmem_st_32x32(pa, reinterpret_cast<const uint32_t(&)[32]>(pk[0]));
+        else if constexpr (CK == 32) tmem_st_32x16(pa, reinterpret_cast<const uint32_t(&)[16]>(pk[0]));
+        else tmem_st_32x8(pa, reinterpret_cast<const uint32_t(&)[8]>(pk[0]));
         BLB_TRACE(g, 4 + c);
-        if (KX > 0 && c == PCH - 1) {
-          uint32_t pt[4] = {0u, 0u, 0u, 0u};
-          if (tail_key0 < T) {        // group 1's tail columns (keys 264..271) are always padding
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float p0 = (tail_key0 + j < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j]), scale_log2, -ms)) : 0.f;
-              const float p1 =
-                  (tail_key0 + j + 1 < T) ? ex2_approx(fmaf(__uint_as_float(sv[128 + j + 1]), scale_log2, -ms)) : 0.f;
-              pt[j / 2] = pack_bf16x2(p0, p1);
-              l0 += p0; l1 += p1;
-            }
-          }
-          tmem_st_32x4(lane_addr + Cfg::P_COL + tail_key0 / 2, pt);
-        }
+        if (has_tail && c == PCH - 1) tmem_st_32x8(lane_addr + Cfg::P_COL + KMAIN / 2, pt);
       }
-      sts_f32(psum + ((g & 1) * 2 * QT + wg * QT + row) * 4, (l0 + l1) + (l2 + l3));
+      sts_f32(psum + (((g & 1) * NSG + wg) * QT + row) * 4, (l0 + l1) + hsum_f32x2(fadd2(l01, l23)));
       tmem_st_wait();               // the last chunk of P is in TMEM
       tc_fence_before();
       __syncwarp();
@@ -808,7 +896,9 @@ attention_tc_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __rest
   __syncthreads();
   if (warp == W_ALLOC) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base_ld(), 512);
+    uint32_t tb;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tb) : "r"(smem_u32(&s_params[1])));
+    tmem_dealloc<1>(tb, 512);
   }
 }
 

@@ -25,6 +25,10 @@
 #include "gemm.h"
 #include "ptx.cuh"
 
+#ifndef BLB_GEMM_EPI_SLEEP_NS
+#define BLB_GEMM_EPI_SLEEP_NS 0
+#endif
+
 namespace blb {
 
 constexpr int BM = 128;          // rows per CTA (UMMA M = 128 per CTA; 256 for a CTA pair)
@@ -339,7 +343,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
       }
 
+#if BLB_GEMM_EPI_SLEEP_NS > 0
+      // A/B switch: poll with test_wait + nanosleep instead of parking the 8 epilogue warps in try_wait
+      mbar_wait_sleep<BLB_GEMM_EPI_SLEEP_NS>(&tfull_bar[acc], acc_phase);
+#else
       mbar_wait(&tfull_bar[acc], acc_phase);
+#endif
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {

@@ -6,31 +6,35 @@
 // One persistent CTA per SM walks (image, head) units; per unit it handles the first 256 query rows as two
 // 128-row tiles and — DINOv2 only — the T-256 = 5 remaining query rows as a third "tail" tile against the K/V that
 // are already in shared memory.  The tail tile's Q rows are REPLICATED into all four TMEM lane quarters (four 8-row
-// TMA boxes), so that all eight softmax warps share its 261 score columns (34 each); every warp zero-fills the P
+// TMA boxes), so that all softmax warps share its 261 score columns (34 each for eight warps); every warp zero-fills the P
 // columns it does not own, the four quarters' partial O / row sums are added through shared memory.
 //
-// The kernel's ceiling is the MUFU pipe (one exp2 per score, 16/clk/SM), so the warps that feed it do nothing else:
+// Two floors bound the kernel, within 20 % of each other: the MUFU pipe (one exp2 per score, 16/clk/SM) and HBM (the
+// packed qkv tensor read once, the output written once: 547 / 604 MB per launch at B = 256).  The warps that feed the
+// MUFU pipe do nothing else (warp ids for the default NSG = 2 softmax warpgroups):
 //
-//   warps 0-7    softmax: two groups of 4 warps split the S columns; a thread owns query row = TMEM lane.  It pulls
+//   warps 0-7    softmax: NSG groups of 4 warps split the S columns; a thread owns query row = TMEM lane.  It pulls
 //                its slice of the S row into registers with ONE pass of tcgen05.ld and releases S at once (s_free) —
 //                the next tile's Q·Kᵀ runs on the tensor pipe underneath this tile's softmax — reads the row max that
-//                the helper warps prepared, then exp2 → bf16 P → tcgen05.st, published chunk by chunk.
+//                the helper warps prepared, then exp2 (+ the fp32 row sum, packed f32x2 adds) → bf16 P → tcgen05.st,
+//                published chunk by chunk.
 //   warp 8       TMA producer: Q tiles, K, V straight out of the packed QKV GEMM output through a 4-D tensor map
 //                {d, 3·H head slots, token, image}; rows >= T and d >= head_dim are zero-filled by TMA (OOB);
 //                K and V are double-buffered across units
 //   warp 9       MMA issuer:   S = Q·Kᵀ  (SS: M128 × N256[+16], fp32 in TMEM columns [0, 256+KX))
 //                              O = P·V   (TS: A = bf16 P in TMEM, B = V as an MN-major smem operand), issued chunk
-//                              by chunk under the exp2 stream;  row sums = P·1 on the tensor pipe
+//                              by chunk under the exp2 stream
 //   warp 10      TMEM allocator   (warp 11 idles; setmaxnreg is warpgroup-granular)
-//   warps 12-15  helpers (round 2, one per TMEM lane quarter), everything that is neither MUFU nor MMA:
+//   warps 12-15  helpers (one per TMEM lane quarter), everything that is neither MUFU nor MMA:
 //                  row max of S(g+2) over all key columns → shared memory (two tiles ahead of the softmax warps:
 //                  S(g+1) is in TMEM long before softmax(g) ends), and the epilogue of tile g: O / rowsum → bf16 →
 //                  swizzled smem staging → coalesced 128-byte row stores.
-//                Round 1/early round 2 had the softmax warps do both (max exchange through a 64-thread barrier, the
-//                epilogue threaded through the exp2 stream): the two softmax warps of a sub-partition run in lock
-//                step, so every non-MUFU phase left the MUFU pipe idle for both (tile ≈ 4500 cycles against a MUFU
-//                floor of 2176).
-//   TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [.., +(256+KX)/2) | O fp32 [.., +64/80) | row sums [.., +16)
+//                Round 1 / early round 2 had the softmax warps do both (max exchange through a 64-thread barrier, the
+//                epilogue threaded through the exp2 stream): the softmax warps of a sub-partition run in lock step,
+//                so every non-MUFU phase left the MUFU pipe idle for all of them (tile ≈ 4500 cycles against a MUFU
+//                floor of 2176; ≈ 3000 now).
+//   TMEM columns: S fp32 [0, 256+KX) | P bf16x2 [.., +(256+KX)/2) | O fp32 [.., +64/80)   (40 / 48 columns spare)
+// DESIGN.md §4.3 has the measurements behind each of these choices and the list of what was tried and dropped.
 #include <algorithm>
 #include <cmath>
 
@@ -53,7 +57,7 @@ static_assert(NSG == 2 || NSG == 4, "NSG");
 constexpr int CG = KMAIN / NSG;     // main S columns per softmax group
 constexpr int NSW = 4 * NSG;        // softmax warps
 constexpr int TC_THREADS = 128 * (NSG + 2);   // softmax warpgroups + 4 control warps + 4 helper (row max / epilogue) warps
-// register budgets per thread (setmaxnreg; the three must add up to 512 = 65536 / 128 over all warpgroups)
+// register budgets per thread (setmaxnreg), summed over the warpgroups they may not exceed what the CTA was launched with
 constexpr int REG_SOFTMAX = NSG == 2 ? 176 : 88, REG_CONTROL = NSG == 2 ? 56 : 40, REG_HELPER = NSG == 2 ? 104 : 88;
 constexpr int REG_LAUNCH = (65536 / TC_THREADS) / 8 * 8;   // what every thread owns when the kernel starts
 // setmaxnreg moves registers inside the CTA's own allocation (threads x REG_LAUNCH), not the SM's file: an increase

@@ -52,9 +52,9 @@ NCU_DRAM_BYTES_PER_LAUNCH = {
     (0, 3072, 1024, 1, 0): 147.46e6 + 362.11e6,     # DINOv2 qkv   (algorithmic: A 137 + W 6 + out 410 MB)
     (1, 4096, 1024, 1, 0): 149.58e6 + 496.06e6,     # DINOv2 fc1   (A 137 + W 8 + out 547 MB)
     (2, 1024, 4096, 0, 1): 928.53e6 + 378.77e6,     # DINOv2 fc2   (A 547 + W 8 + resid 274 r + 274 w + bf16 copy 137 MB)
-    (2, 1024, 1024, 0, 1): 415.44e6 + 362.06e6,     # DINOv2 proj  (A 137 + W 2 + resid 274 r + 274 w + bf16 copy 137 MB)
-    (1, 4352, 1152, 1, 0): 167.40e6 + 524.24e6,     # SigLIP fc1   (A 151 + W 10 + out 570 MB)
-    (2, 1152, 4352, 0, 1): 948.67e6 + 425.22e6,     # SigLIP fc2   (A 570 + W 10 + resid 302 r + 302 w + bf16 copy 151 MB)
+    (2, 1024, 1024, 0, 1): 414.92e6 + 360.50e6,     # DINOv2 proj  (A 137 + W 2 + resid 274 r + 274 w + bf16 copy 137 MB)   [r02]
+    (1, 4352, 1152, 1, 0): 167.39e6 + 521.80e6,     # SigLIP fc1   (A 151 + W 10 + out 570 MB)   [r02]
+    (2, 1152, 4352, 0, 1): 939.50e6 + 424.58e6,     # SigLIP fc2   (A 570 + W 10 + resid 302 r + 302 w + bf16 copy 151 MB)   [r02]
 }
 
 
@@ -440,7 +440,7 @@ def run_gpu(args) -> None:
             "flops_per_launch": twork / cnt, "avg_launch_us": 1e3 * tms_ / cnt, "launches_per_step": cnt // 2,
             "share_of_step": (tms_ / 2) / ms_per_step,
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((mode, Nn, Kk, lnf, st)) if B == 256 else None,
-            "traffic_source": "profiles/r01_ncu_full_c_kernels.md (ncu --set full, dram__bytes_read+write per launch, B=256)",
+            "traffic_source": "profiles/r02_ncu_gemm.md / r01_ncu_full_c_kernels.md (ncu --set full, dram__bytes_read+write per launch, B=256)",
             "gemm_family": {"achieved": family, "frac": family / peak, "note": "all tcgen05 GEMM launches of the step"},
             "gemm_ms_per_step": g["ms"] / 2, "gemm_launches_per_step": g["launches"] // 2,
             "whole_step": {"achieved": step_tflops, "frac_of_sustained": step_tflops / peak,

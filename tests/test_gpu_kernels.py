@@ -142,6 +142,26 @@ def test_attention(ops, B, T, H, hd):
     assert _rel(out, ref) < 0.2 * _rel(wrong, ref)
 
 
+@pytest.mark.parametrize("B,T,H,hd", [(256, 261, 16, 64), (256, 256, 16, 72)])
+def test_attention_full_batch_properties(ops, B, T, H, hd):
+    """BASELINE-size launches (every SM walks ~28 units, tail tiles included), checked through size-independent
+    properties: with V = 1 every output is Σp / Σp = 1 (the fp32 row sums of the softmax warps against the bf16 P the
+    PV MMAs consume), and a handful of (image, head) units against fp32 SDPA."""
+    g = _gen(B + T)
+    D = H * hd
+    qkv = torch.randn(B * T, 3 * D, device="cuda", generator=g).bfloat16()
+    out = ops.attention(qkv, B, T, H, hd)
+    q, k, v = qkv.view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    for b in (0, 97, B - 1):                                   # first / middle / last image, all heads
+        ref = F.scaled_dot_product_attention(q[b:b + 1].float(), k[b:b + 1].float(), v[b:b + 1].float())
+        ref = ref.transpose(1, 2).reshape(T, D)
+        assert _rel(out[b * T:(b + 1) * T], ref) < 6e-3, b
+    ones = qkv.clone()
+    ones.view(B, T, 3, H, hd)[:, :, 2] = 1.0
+    out1 = ops.attention(ones, B, T, H, hd).float()
+    assert (out1 - 1.0).abs().max().item() <= 2.0 ** -7        # 1 ± one bf16 ulp
+
+
 def test_im2col_matches_unfold_and_conv_weight_order(ops):
     g = _gen(1)
     px = torch.randn(3, 3, 224, 224, device="cuda", generator=g).bfloat16()

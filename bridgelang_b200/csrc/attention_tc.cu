@@ -136,7 +136,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x2(uint32_t taddr, const uint32_t (&r)[2]) {
+[[maybe_unused]] __device__ __forceinline__ void tmem_st_32x2(uint32_t taddr, const uint32_t (&r)[2]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -265,7 +265,7 @@ __device__ __forceinline__ void slack_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t (&r)[2]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 

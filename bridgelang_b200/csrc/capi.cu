@@ -67,6 +67,10 @@ int check_vit(const blb_vit_weights* w) {
 // side stream + fork/join events for running the two towers concurrently (one set per device, created lazily;
 // BLB_NO_TOWER_OVERLAP=1 runs them back to back on the caller's stream)
 const bool g_tower_overlap = getenv("BLB_NO_TOWER_OVERLAP") == nullptr;
+// Lifetime: one stream + two events per (host thread, device), kept until the process ends.  They are deliberately NOT
+// destroyed from a thread_local destructor: for the main thread that destructor runs during process teardown, possibly
+// after the (statically linked) CUDA runtime has shut down, where CUDA calls are undefined — a few hundred bytes of
+// driver state per serving thread is the cheaper side of that trade.
 struct TowerOverlap {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;

@@ -142,6 +142,30 @@ def test_attention(ops, B, T, H, hd):
     assert _rel(out, ref) < 0.2 * _rel(wrong, ref)
 
 
+@pytest.mark.parametrize("B,T,H,hd", [(4, 261, 16, 64), (4, 256, 16, 72)])
+def test_attention_peaked_and_flat_rows(ops, B, T, H, hd):
+    """Rows far from the N(0,1) logits of the other tests: nearly one-hot softmax rows (logit std ≈ 40: every exp2
+    argument but a few is flushed to zero, the row sum is ≈ 1) and exactly flat rows (q = 0: every p is 1, the row sum is
+    T, the output is the mean of V) — the fp32 row sums of the softmax warps, the masked tail-block keys and the
+    helpers' row max at both extremes."""
+    g = _gen(7 * T + hd)
+    D = H * hd
+    qkv = torch.randn(B * T, 3 * D, device="cuda", generator=g)
+    v5 = qkv.view(B, T, 3, H, hd)
+    v5[:, :, 0] *= 18.0                                      # q
+    v5[:, :, 1] *= 18.0                                      # k  → logits·scale with std ≈ 18·18·sqrt(hd)/sqrt(hd)
+    v5[1, :, 0] = 0.0                                        # image 1: flat rows
+    qkv = qkv.bfloat16()
+    out = ops.attention(qkv, B, T, H, hd)
+    assert torch.isfinite(out.float()).all()
+    q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, D)
+    assert _rel(out, ref) < 1e-2
+    flat = out.view(B, T, D)[1].float()
+    mean_v = v[1].mean(dim=1).reshape(1, D)                  # [H, hd] → [1, D]
+    assert (flat - mean_v).abs().max().item() < 2e-2 * max(mean_v.abs().max().item(), 1e-3) + 4e-3
+
+
 @pytest.mark.parametrize("B,T,H,hd", [(256, 261, 16, 64), (256, 256, 16, 72)])
 def test_attention_full_batch_properties(ops, B, T, H, hd):
     """BASELINE-size launches (every SM walks ~28 units, tail tiles included), checked through size-independent
